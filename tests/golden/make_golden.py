@@ -131,6 +131,9 @@ def gen_rife():
     from drba_b200.weights import synth_ifnet_state, load_ifnet_state
 
     torch.set_grad_enabled(False)
+    # importing the reference's torch splat flips this to "medium" process-wide
+    # (softsplat_torch.py:13), which lets oneDNN run fp32 convs in bf16; undo it
+    torch.set_float32_matmul_precision("highest")
     rng = np.random.default_rng(77)
     H, W = 64, 128
 
