@@ -1,0 +1,129 @@
+/*
+ * drba_b200.h -- C ABI of libdrba_b200.so (sm_100a).
+ *
+ * This is the drop-in boundary for DRBA's per-triplet interpolation hot path.
+ * The reference's only FFI precedent is the CuPy launch in
+ * models/softsplat/softsplat.py:362-367 (raw data_ptr()s + dims, caller-allocated
+ * output, torch's current stream); every entry point below keeps that contract:
+ *
+ *   - plain pointers and sizes, no torch / C++ types;
+ *   - all pointers are DEVICE pointers to contiguous tensors (NCHW unless noted);
+ *   - the call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     never allocates, never synchronises, is re-entrant;
+ *   - returns 0, a negative DRBA_E_* argument error, or a positive cudaError_t.
+ *
+ * Workspaces: ops that scatter need a zero-filled accumulator.  The caller owns it.
+ * Contract: a workspace handed to any drba_* op must be all-zero on entry (use
+ * drba_workspace_clear once after allocation); every op leaves it all-zero on exit
+ * (the resolve pass re-zeroes what it reads), so it can be reused without memsets.
+ *
+ * Reference citations are relative to the DRBA checkout (commit a99ce27).
+ */
+#ifndef DRBA_B200_H
+#define DRBA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DRBA_API __attribute__((visibility("default")))
+#else
+#define DRBA_API
+#endif
+
+/* error codes (negative; positive return values are cudaError_t) */
+#define DRBA_OK 0
+#define DRBA_E_ARG (-1)         /* NULL / non-positive dimension / bad enum        */
+#define DRBA_E_WORKSPACE (-2)   /* workspace missing or too small                  */
+#define DRBA_E_UNSUPPORTED (-3) /* valid request this build cannot serve           */
+#define DRBA_E_ALIGN (-4)       /* pointer not aligned as required (16 B)          */
+
+/* softsplat modes / eps variants: models/softsplat/softsplat.py:260-267, :273-290 */
+enum { DRBA_SPLAT_SUM = 0, DRBA_SPLAT_AVG = 1, DRBA_SPLAT_LINEAR = 2, DRBA_SPLAT_SOFT = 3 };
+enum { DRBA_EPS_ADD = 0, DRBA_EPS_ZERO = 1, DRBA_EPS_CLIP = 2 };
+/* padding of the backward warp: warplayer.py:22 (border) / MetricNet.py:20 (zeros) */
+enum { DRBA_PAD_BORDER = 0, DRBA_PAD_ZEROS = 1 };
+/* activation dtypes of the conv engine */
+enum { DRBA_F32 = 0, DRBA_F16 = 1 };
+
+DRBA_API int drba_version(void);
+DRBA_API const char* drba_error_string(int code);
+/* zero-fill a workspace (once, after allocation) */
+DRBA_API int drba_workspace_clear(void* ws, size_t bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * softsplat(tenIn, tenFlow, tenMetric, strMode)
+ * replaces models/softsplat/softsplat.py:248-293 + kernel :306-357
+ * (twin: softsplat_torch.py:20-179).  fp32 NCHW: in [N,C,H,W], flow [N,2,H,W]
+ * (ch0 = x, ch1 = y, pixels), metric [N,1,H,W] or NULL (sum/avg), out [N,C,H,W].
+ * The accumulator lives in `ws` (channel-interleaved groups of 4, L2 resident);
+ * larger C is processed in channel chunks sized to the workspace given.
+ * ------------------------------------------------------------------------- */
+DRBA_API size_t drba_softsplat_workspace_bytes(int N, int C, int H, int W, int mode);
+DRBA_API int drba_softsplat_f32(const float* in, const float* flow, const float* metric, float* out,
+                                int N, int C, int H, int W, int mode, int eps_mode,
+                                void* ws, size_t ws_bytes, void* stream);
+/* variant selector for measurements: 0 = aggregated vector reds (default),
+ * 1 = one scalar atomic per corner and channel (the reference kernel's scheme) */
+DRBA_API int drba_softsplat_f32_variant(const float* in, const float* flow, const float* metric, float* out,
+                                        int N, int C, int H, int W, int mode, int eps_mode,
+                                        void* ws, size_t ws_bytes, int variant, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * RIFE.calc_flow's flow inversion, models/rife.py:59-73:
+ *   out = 2 * fill(-splat_avg(flow_t0, flow_t0), holes <- max(H, W))
+ * flow_t0, out: [N,2,H,W] fp32.  ws >= N*H*W*16 bytes.
+ * ------------------------------------------------------------------------- */
+DRBA_API size_t drba_rife_invert_flow_workspace_bytes(int N, int H, int W);
+DRBA_API int drba_rife_invert_flow_f32(const float* flow_t0, float* out, int N, int H, int W,
+                                       void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * get_drm_t(drm, t, precision): models/drm.py:10-62.  n elements, fp32.
+ * ------------------------------------------------------------------------- */
+DRBA_API int drba_get_drm_t_f32(const float* drm, double t, double precision, float* out, size_t n, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * calc_drm_rife (models/drm.py:65-107) and calc_drm_rife_auxiliary (:158-195)
+ * fused with distance_calculator (models/utils/tools.py:77-80).
+ * flow10, flow12 [N,2,H,W]; metric10/metric12 [N,1,H,W] or both NULL ('avg');
+ * out_t01 ('drm_t1_t01') / out_t12 ('drm_t1_t12') [N,1,H,W]; either may be NULL
+ * when the caller needs only one map.  ws >= N*H*W*16 bytes.
+ * ------------------------------------------------------------------------- */
+DRBA_API size_t drba_drm_workspace_bytes(int N, int H, int W);
+DRBA_API int drba_drm_rife_f32(double t, const float* flow10, const float* flow12,
+                               const float* metric10, const float* metric12, int linear,
+                               float* out_t01, float* out_t12, int N, int H, int W,
+                               void* ws, size_t ws_bytes, void* stream);
+/* calc_drm_gmfss (models/drm.py:110-155).  Outputs in the reference's dict order;
+ * any may be NULL.  No epsilon on the distances: 0/0 = NaN propagates as in the
+ * reference. */
+DRBA_API int drba_drm_gmfss_f32(double t, const float* flow10, const float* flow12,
+                                const float* metric10, const float* metric12, int linear,
+                                float* drm0t_t01, float* drm1t_t01, float* drm1t_t12, float* drm2t_t12,
+                                int N, int H, int W, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Backward warp (grid_sample bilinear, align_corners=True) in pixel coordinates:
+ * models/rife_426_heavy/warplayer.py:8-22 (border), models/model_gmfss/MetricNet.py:10-20
+ * and models/gmflow/geometry.py:60-67 (zeros).  in/out [N,C,H,W], flow [N,2,H,W].
+ * ------------------------------------------------------------------------- */
+DRBA_API int drba_backwarp_f32(const float* in, const float* flow, float* out,
+                               int N, int C, int H, int W, int pad_mode, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * F.interpolate(mode='bilinear'): IFNet_HDv3.py:85-92, tools.py:72, GMFSS.py:64-77.
+ * rh/rw = source-per-destination ratio (1/scale_factor, or in/out when a size is
+ * given); ignored when align_corners != 0.
+ * ------------------------------------------------------------------------- */
+DRBA_API int drba_resize_bilinear_f32(const float* in, float* out, int N, int C, int H, int W,
+                                      int OH, int OW, int align_corners, float rh, float rw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRBA_B200_H */

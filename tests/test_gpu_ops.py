@@ -1,0 +1,242 @@
+"""GPU parity of the HBM-bound operators (called through the C ABI via the host mirrors)
+against the CPU oracle and the reference-generated golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cport
+
+pytestmark = pytest.mark.gpu
+
+SPLAT_MODES = ["sum", "avg", "linear", "soft", "avg-zeroeps", "soft-clipeps", "linear-addeps"]
+# fp32 atomics are order-nondeterministic: sums of <= ~20 products differ in the last bits
+SPLAT_TOL = dict(rtol=2e-5, atol=2e-6)
+
+
+def cu(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _metric_for(mode, g, name):
+    return None if mode.split("-")[0] in ("sum", "avg") else g[f"splat_{name}_metric"]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("mode", SPLAT_MODES)
+def test_softsplat_vs_reference_golden(golden_ops, mode, variant):
+    from drba_b200.softsplat import softsplat
+    g = golden_ops
+    for name in g["splat_cases"]:
+        m = _metric_for(mode, g, name)
+        got = softsplat(cu(g[f"splat_{name}_in"]), cu(g[f"splat_{name}_flow"]), cu(m), mode, _variant=variant)
+        want = g[f"splat_{name}_{mode}"]
+        # normalised outputs divide by sums that can be ~1e-7: compare where the oracle is well
+        # conditioned with a relative bound, everywhere with a bound scaled by the output magnitude
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * max(1.0, float(np.abs(want).max())),
+                                   err_msg=f"{name} {mode}")
+
+
+@pytest.mark.parametrize("mode", ["sum", "avg", "linear", "soft"])
+@pytest.mark.parametrize("shape", [(1, 1, 64, 96), (2, 3, 33, 47), (1, 7, 128, 160), (1, 64, 40, 56)])
+def test_softsplat_vs_oracle_seeded(mode, shape):
+    from drba_b200.softsplat import softsplat
+    rng = np.random.default_rng(hash((mode, shape)) % (2 ** 32))
+    n, c, h, w = shape
+    x = rng.standard_normal(shape).astype(np.float32)
+    # smooth flow + noise: exercises both the chained (aggregated) and the unchained path
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    flow = np.stack([3.3 * np.sin(yy / 9) + 0.2 * xx / w, 2.1 * np.cos(xx / 7)], 0)[None].repeat(n, 0)
+    flow = (flow + 0.05 * rng.standard_normal(flow.shape)).astype(np.float32)
+    flow[:, :, : h // 4, : w // 4] += 30 * rng.standard_normal((n, 2, h // 4, w // 4)).astype(np.float32)
+    metric = None if mode in ("sum", "avg") else (0.5 * rng.standard_normal((n, 1, h, w))).astype(np.float32)
+    want = cport.softsplat(x, flow, metric, mode)
+    got = softsplat(cu(x), cu(flow), cu(metric), mode).cpu().numpy()
+    if mode == "sum":
+        np.testing.assert_allclose(got, want, **SPLAT_TOL)
+    else:
+        # well-conditioned pixels (weight sum not tiny) must agree tightly
+        den = cport.softsplat(np.ones((n, 1, h, w), np.float32), flow, metric, "sum" if metric is None else mode)
+        wsum = cport.softsplat(np.ones((n, 1, h, w), np.float32), flow, None, "sum")
+        good = np.broadcast_to(wsum > 1e-3, want.shape)
+        np.testing.assert_allclose(got[good], want[good], rtol=1e-4, atol=1e-5)
+        assert np.isfinite(got).all()
+
+
+def test_softsplat_edge_cases():
+    from drba_b200.softsplat import softsplat
+    x = torch.ones((1, 2, 4, 5), device="cuda")
+    flow = torch.full((1, 2, 4, 5), 100.0, device="cuda")
+    assert torch.all(softsplat(x, flow, None, "sum") == 0)
+    assert torch.all(softsplat(x, flow, None, "avg") == 0)
+    flow[:] = float("nan")
+    assert torch.all(softsplat(x, flow, None, "sum") == 0)
+    flow[:] = float("inf")
+    assert torch.all(softsplat(x, flow, None, "avg") == 0)
+    z = softsplat(torch.zeros((1, 1, 1, 1), device="cuda"), torch.zeros((1, 2, 1, 1), device="cuda"), None, "avg")
+    assert z.shape == (1, 1, 1, 1)
+    e = softsplat(torch.zeros((1, 0, 4, 4), device="cuda"), torch.zeros((1, 2, 4, 4), device="cuda"), None, "sum")
+    assert e.shape == (1, 0, 4, 4)
+    # identity flow reproduces the input exactly (single corner with weight 1)
+    y = torch.rand((1, 3, 8, 8), device="cuda")
+    assert torch.equal(softsplat(y, torch.zeros((1, 2, 8, 8), device="cuda"), None, "sum"), y)
+    # dtype round trip (softsplat.py:293)
+    h = softsplat(y.half(), torch.zeros((1, 2, 8, 8), device="cuda").half(), None, "avg")
+    assert h.dtype == torch.float16
+    # the workspace invariant (zero on exit): a second call gives the same answer
+    a = softsplat(y, 2.5 * torch.ones((1, 2, 8, 8), device="cuda"), None, "avg")
+    b = softsplat(y, 2.5 * torch.ones((1, 2, 8, 8), device="cuda"), None, "avg")
+    assert torch.equal(a, b)
+    with pytest.raises(AssertionError):
+        softsplat(y, flow[:, :, :1, :1], None, "soft")
+    with pytest.raises(Exception):
+        softsplat(y.cpu(), torch.zeros((1, 2, 8, 8)), None, "sum")   # no CPU fallback
+
+
+def test_softsplat_chunked_matches_unchunked():
+    """C large enough that the accumulator is processed in channel chunks."""
+    from drba_b200 import _lib
+    from drba_b200._torch_util import stream_ptr
+    L = _lib.lib()
+    n, c, h, w = 1, 11, 48, 64
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn((n, c, h, w), generator=g).cuda()
+    flow = (4 * torch.randn((n, 2, h, w), generator=g)).cuda()
+    m = torch.randn((n, 1, h, w), generator=g).cuda()
+    big = torch.zeros(n * h * w * 16 * 3, dtype=torch.uint8, device="cuda")
+    small = torch.zeros(n * h * w * 16, dtype=torch.uint8, device="cuda")   # one group: 3 channels per chunk
+    o1, o2 = torch.empty_like(x), torch.empty_like(x)
+    for ws, o in ((big, o1), (small, o2)):
+        rc = L.drba_softsplat_f32(x.data_ptr(), flow.data_ptr(), m.data_ptr(), o.data_ptr(), n, c, h, w, 3, 0,
+                                  ws.data_ptr(), ws.numel(), stream_ptr())
+        assert rc == 0
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(o1.cpu().numpy(), o2.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    assert int(big.count_nonzero()) == 0 and int(small.count_nonzero()) == 0   # zero on exit
+    want = cport.softsplat(x.cpu().numpy(), flow.cpu().numpy(), m.cpu().numpy(), "soft")
+    np.testing.assert_allclose(o2.cpu().numpy(), want, rtol=1e-3, atol=1e-4)
+
+
+def test_c_abi_argument_errors():
+    from drba_b200 import _lib
+    L = _lib.lib()
+    x = torch.zeros((1, 1, 4, 4), device="cuda")
+    f = torch.zeros((1, 2, 4, 4), device="cuda")
+    assert L.drba_softsplat_f32(x.data_ptr(), f.data_ptr(), None, x.data_ptr(), 1, 1, 4, 4, 1, 0, None, 0, None) == -2
+    assert L.drba_softsplat_f32(x.data_ptr(), f.data_ptr(), None, x.data_ptr(), 1, 1, 4, 4, 9, 0, None, 0, None) == -1
+    assert L.drba_softsplat_f32(x.data_ptr(), f.data_ptr(), None, x.data_ptr(), 1, 1, 4, 4, 3, 0, None, 0, None) == -1
+    assert L.drba_softsplat_f32(None, None, None, None, 1, 0, 4, 4, 0, 0, None, 0, None) == 0
+    assert L.drba_backwarp_f32(x.data_ptr(), f.data_ptr(), x.data_ptr(), 1, 1, 4, 4, 7, None) == -1
+    assert b"workspace" in L.drba_error_string(-2)
+
+
+@pytest.mark.parametrize("t", [0.2, 0.4, 0.5])
+@pytest.mark.parametrize("linear", [True, False])
+def test_drm_vs_reference_golden(golden_ops, t, linear):
+    from drba_b200 import drm
+    g = golden_ops
+    tol = dict(rtol=0, atol=3e-6)
+    for name in g["drm_cases"]:
+        f10, f12 = cu(g[f"drm_{name}_f10"]), cu(g[f"drm_{name}_f12"])
+        m10, m12 = cu(g[f"drm_{name}_m10"]), cu(g[f"drm_{name}_m12"])
+        tag = f"drm_{name}_t{t}_{'lin' if linear else 'nl'}"
+        r = drm.calc_drm_rife(t, f10, f12, linear)
+        for k, v in r.items():
+            np.testing.assert_allclose(v.cpu().numpy(), g[f"{tag}_rife_{k}"], err_msg=f"{tag} rife {k}", **tol)
+        for k in ("drm_t1_t01", "drm_t1_t12"):   # single-map extension gives the same map
+            one = drm.calc_drm_rife(t, f10, f12, linear, only=k)
+            assert list(one) == [k]
+            np.testing.assert_allclose(one[k].cpu().numpy(), g[f"{tag}_rife_{k}"], **tol)
+        a = drm.calc_drm_rife_auxiliary(t, f10, f12, m10, m12, linear)
+        for k, v in a.items():
+            np.testing.assert_allclose(v.cpu().numpy(), g[f"{tag}_aux_{k}"], err_msg=f"{tag} aux {k}", rtol=0, atol=1e-5)
+        gm = drm.calc_drm_gmfss(t, f10, f12, m10, m12, linear)
+        for k, v in gm.items():
+            np.testing.assert_allclose(v.cpu().numpy(), g[f"{tag}_gmfss_{k}"], err_msg=f"{tag} gmfss {k}", rtol=0, atol=1e-5)
+        g0 = drm.calc_drm_gmfss(t, f10, f12, None, None, linear)
+        for k, v in g0.items():
+            np.testing.assert_allclose(v.cpu().numpy(), g[f"{tag}_gmfssavg_{k}"], err_msg=f"{tag} gmfss-avg {k}", **tol)
+
+
+def test_drm_gmfss_nan_quirk(golden_ops):
+    from drba_b200 import drm
+    g = golden_ops
+    m = cu(g["drm_nan_m"])
+    got = drm.calc_drm_gmfss(0.4, cu(g["drm_nan_f10"]), cu(g["drm_nan_f12"]), m, m, True)
+    for k, v in got.items():
+        v = v.cpu().numpy()
+        want = g[f"drm_nan_{k}"]
+        assert np.isnan(want).sum() > 0
+        np.testing.assert_array_equal(np.isnan(v), np.isnan(want), err_msg=k)
+        np.testing.assert_allclose(v[~np.isnan(want)], want[~np.isnan(want)], rtol=0, atol=1e-5, err_msg=k)
+
+
+@pytest.mark.parametrize("t", [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.8, 0.95])
+def test_get_drm_t(golden_ops, t):
+    from drba_b200 import drm
+    g = golden_ops
+    np.testing.assert_array_equal(drm.get_drm_t(cu(g["gdt_in"]), t).cpu().numpy(), g[f"gdt_t{t}"])
+
+
+def test_drm_rife_1080p_properties():
+    """Full BASELINE size (1088x1920): properties that need no oracle run."""
+    from drba_b200 import drm
+    h, w = 1088, 1920
+    g = torch.Generator(device="cpu").manual_seed(0)
+    base = torch.nn.functional.interpolate(6 * torch.randn((1, 2, h // 16, w // 16), generator=g), size=(h, w),
+                                           mode="bilinear", align_corners=False)
+    f10, f12 = base.cuda(), (-0.7 * base + 0.3).cuda()
+    r = drm.calc_drm_rife(0.4, f10, f12, True)
+    a, b = r["drm_t1_t01"], r["drm_t1_t12"]
+    assert a.shape == (1, 1, h, w) and torch.isfinite(a).all() and torch.isfinite(b).all()
+    # a forward-warped average of values in [lo, hi] stays in [lo, hi]; holes are filled from the same range
+    d10 = f10.pow(2).sum(1, keepdim=True).sqrt() + 1e-4
+    d12 = f12.pow(2).sum(1, keepdim=True).sqrt() + 1e-4
+    u1 = d12 / (d10 + d12) * 0.4 * 2
+    u0 = d10 / (d10 + d12) * 0.4 * 2
+    assert a.min() >= u1.min() - 1e-5 and a.max() <= u1.max() + 1e-5
+    assert b.min() >= u0.min() - 1e-5 and b.max() <= u0.max() + 1e-5
+    # zero flows: nothing moves, the aligned map equals the unaligned one
+    z = torch.zeros_like(f10)
+    rz = drm.calc_drm_rife(0.3, z, z, True)
+    assert torch.allclose(rz["drm_t1_t01"], torch.full_like(a, 0.3), atol=1e-6)
+    # run-to-run agreement (atomics): same result within a few ulp
+    r2 = drm.calc_drm_rife(0.4, f10, f12, True)
+    assert torch.allclose(r2["drm_t1_t01"], a, atol=1e-5)
+
+
+def test_backwarp(golden_ops):
+    from drba_b200.ops import backwarp
+    g = golden_ops
+    x, f = cu(g["bw_in"]), cu(g["bw_flow"])
+    np.testing.assert_allclose(backwarp(x, f, "border").cpu().numpy(), g["bw_border"], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(backwarp(x, f, "zeros").cpu().numpy(), g["bw_zeros"], rtol=0, atol=3e-5)
+    np.testing.assert_allclose(backwarp(x, f, "border").cpu().numpy(), cport.backwarp(g["bw_in"], g["bw_flow"], "border"),
+                               rtol=0, atol=1e-6)
+
+
+def test_resize(golden_ops):
+    from drba_b200.ops import resize_bilinear
+    g = golden_ops
+    x = cu(g["rs_in"])
+    for sf in [0.0625, 0.125, 0.25, 0.5, 2.0, 4.0]:
+        np.testing.assert_allclose(resize_bilinear(x, scale_factor=sf).cpu().numpy(), g[f"rs_sf{sf}"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(resize_bilinear(x, size=(27, 41)).cpu().numpy(), g["rs_size_27_41"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(resize_bilinear(x, size=(27, 41), align_corners=True).cpu().numpy(),
+                               g["rs_ac_27_41"], rtol=0, atol=1e-5)
+
+
+def test_rife_invert_flow():
+    from drba_b200.ops import rife_invert_flow
+    rng = np.random.default_rng(5)
+    h, w = 64, 96
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    flow = np.stack([4 * np.sin(yy / 11), 3 * np.cos(xx / 13)], 0)[None].astype(np.float32)
+    flow[:, :, 10:20, 10:30] += 15
+    flow += 0.01 * rng.standard_normal(flow.shape).astype(np.float32)
+    want = cport.rife_invert_flow(flow)
+    got = rife_invert_flow(cu(flow)).cpu().numpy()
+    hole_w, hole_g = want == 2 * max(h, w), got == 2 * max(h, w)
+    # hole decisions sit on a threshold (mask < 0.999): allow a handful of borderline flips
+    assert (hole_w != hole_g).sum() <= 4
+    ok = ~(hole_w | hole_g)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=1e-4, atol=1e-4)
