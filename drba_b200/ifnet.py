@@ -1,0 +1,220 @@
+"""IFNet 4.26-heavy engine: host-side orchestration of the CUDA kernels in libdrba_b200.so.
+
+Mirrors models/rife_426_heavy/IFNet_HDv3.py (IFNet.forward :126-177, IFBlock :62-96, Head
+:28-47, ResConv :50-59) for the inference branch the DRBA wrappers use (batch 1).  No torch
+compute ops run here: torch only owns the device buffers and the stream.
+
+Per refinement block:   assemble (warp+cat+resize, 1 kernel) -> conv0a -> conv0b -> 8 x ResConv
+-> lastconv (ConvTranspose + PixelShuffle) -> upsample/accumulate (1 kernel); then one blend
+kernel.  Two conv engines share this schedule:
+  precision="fp32": csrc/conv_direct.cu (CUDA cores, exact reference arithmetic up to summation order)
+  precision="fp16": csrc/conv_tc.cu (tcgen05 implicit GEMM, fp16 operands / fp32 accumulate -- the
+                    reference's own GPU precision under torch.autocast, models/rife.py:26)
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._torch_util import ptr, require_cuda, stream_ptr
+
+_BLOCKS = [("block0", 39, 192), ("block1", 52, 128), ("block2", 52, 96), ("block3", 52, 64), ("block4", 52, 32)]
+
+_LL4 = ctypes.c_longlong * 4
+
+
+def _taps3x3():
+    dy = [ky - 1 for ky in range(3) for kx in range(3)]
+    dx = [kx - 1 for ky in range(3) for kx in range(3)]
+    return dy, dx
+
+
+# ConvTranspose2d(k=4, s=2, p=1): output row 2y+py reads input rows y+dy with kernel row ky
+_CT_PHASE = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}   # py -> [(ky, dy), ...]
+
+
+class _DirectLayer:
+    """One conv layer packed for drba_conv2d_direct_f32: w[T][Cin][Cout]."""
+
+    def __init__(self, w, b, dy, dx, stride, act, device):
+        self.w = w.contiguous().to(device)
+        self.b = b.contiguous().to(device)
+        self.T, self.cin, self.cout = self.w.shape
+        self.dy = (ctypes.c_int * self.T)(*dy)
+        self.dx = (ctypes.c_int * self.T)(*dx)
+        self.stride = stride
+        self.act = act
+
+
+def _pack_conv3x3(weight, bias, beta=None):
+    w = weight.float()
+    b = bias.float()
+    if beta is not None:   # ResConv: conv(x) * beta + x  (IFNet_HDv3.py:58-59) -> fold beta
+        bt = beta.float().reshape(-1)
+        w = w * bt[:, None, None, None]
+        b = b * bt
+    return w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]), b
+
+
+def _pack_convT_phase(weight, py, px):
+    # weight: [Cin, Cout, 4, 4]
+    taps, dy, dx = [], [], []
+    for ky, ddy in _CT_PHASE[py]:
+        for kx, ddx in _CT_PHASE[px]:
+            taps.append(weight[:, :, ky, kx].float())
+            dy.append(ddy)
+            dx.append(ddx)
+    return torch.stack(taps, 0), dy, dx
+
+
+class IFNetEngine:
+    def __init__(self, state, device, precision="fp32"):
+        if precision not in ("fp32", "fp16"):
+            raise ValueError("precision must be 'fp32' or 'fp16'")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.DrbaError("IFNetEngine needs a CUDA device (no CPU fallback)")
+        self.precision = precision
+        self.L = _lib.lib()
+        self._bufs = {}
+        dy9, dx9 = _taps3x3()
+        sd = {k: v.detach().float().cpu() for k, v in state.items()}
+        d = self.device
+        self.direct = {}
+        for name, cin, c in _BLOCKS:
+            w, b = _pack_conv3x3(sd[f"{name}.conv0.0.0.weight"], sd[f"{name}.conv0.0.0.bias"])
+            self.direct[f"{name}.conv0a"] = _DirectLayer(w, b, dy9, dx9, 2, 1, d)
+            w, b = _pack_conv3x3(sd[f"{name}.conv0.1.0.weight"], sd[f"{name}.conv0.1.0.bias"])
+            self.direct[f"{name}.conv0b"] = _DirectLayer(w, b, dy9, dx9, 2, 1, d)
+            for i in range(8):
+                p = f"{name}.convblock.{i}"
+                w, b = _pack_conv3x3(sd[p + ".conv.weight"], sd[p + ".conv.bias"], sd[p + ".beta"])
+                self.direct[f"{name}.res{i}"] = _DirectLayer(w, b, dy9, dx9, 1, 1, d)
+            for py in (0, 1):
+                for px in (0, 1):
+                    w, dy, dx = _pack_convT_phase(sd[f"{name}.lastconv.0.weight"], py, px)
+                    self.direct[f"{name}.last{py}{px}"] = _DirectLayer(w, sd[f"{name}.lastconv.0.bias"], dy, dx, 1, 0, d)
+        for i in range(3):
+            w, b = _pack_conv3x3(sd[f"encode.cnn{i}.weight"], sd[f"encode.cnn{i}.bias"])
+            self.direct[f"encode.cnn{i}"] = _DirectLayer(w, b, dy9, dx9, 2 if i == 0 else 1, 1, d)
+        for py in (0, 1):
+            for px in (0, 1):
+                w, dy, dx = _pack_convT_phase(sd["encode.cnn3.weight"], py, px)
+                self.direct[f"encode.cnn3.{py}{px}"] = _DirectLayer(w, sd["encode.cnn3.bias"], dy, dx, 1, 0, d)
+        self.launches = 0   # kernels launched through this engine (bench.py reports it)
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, key, shape, dtype=torch.float32):
+        t = self._bufs.get(key)
+        if t is None or t.shape != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def _check(self, rc, what):
+        self.launches += 1
+        _lib.check(rc, what)
+
+    def _conv_direct(self, layer, x_ptr, H, W, in_strides, out_t, OH, OW, out_strides, OS=1, PY=0, PX=0, res_ptr=None):
+        rc = self.L.drba_conv2d_direct_f32(x_ptr, ptr(layer.w), ptr(layer.b), res_ptr, ptr(out_t),
+                                           1, layer.cin, H, W, _LL4(*in_strides),
+                                           layer.cout, OH, OW, _LL4(*out_strides),
+                                           layer.stride, OS, PY, PX, layer.T, layer.dy, layer.dx,
+                                           layer.act, stream_ptr(self.device))
+        self._check(rc, "drba_conv2d_direct_f32")
+
+    @staticmethod
+    def _nchw(c, h, w):
+        return (c * h * w, h * w, w, 1)
+
+    # ------------------------------------------------------------------ Head (IFNet_HDv3.py:28-47)
+    def encode(self, img):
+        """img [1,3,H,W] fp32 -> feature map [H][W][16] (NHWC; fp32 in the exact engine)."""
+        require_cuda(img)
+        img = img.float().contiguous()
+        _, _, H, W = img.shape
+        assert H % 2 == 0 and W % 2 == 0
+        h2, w2 = H // 2, W // 2
+        a = self._buf(("enc_a", H, W), (16, h2, w2))
+        b = self._buf(("enc_b", H, W), (16, h2, w2))
+        feat = torch.empty((H, W, 16), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._conv_direct(self.direct["encode.cnn0"], ptr(img), H, W, self._nchw(3, H, W), a, h2, w2, self._nchw(16, h2, w2))
+            self._conv_direct(self.direct["encode.cnn1"], ptr(a), h2, w2, self._nchw(16, h2, w2), b, h2, w2, self._nchw(16, h2, w2))
+            self._conv_direct(self.direct["encode.cnn2"], ptr(b), h2, w2, self._nchw(16, h2, w2), a, h2, w2, self._nchw(16, h2, w2))
+            nhwc = (H * W * 16, 1, W * 16, 16)
+            for py in (0, 1):
+                for px in (0, 1):
+                    self._conv_direct(self.direct[f"encode.cnn3.{py}{px}"], ptr(a), h2, w2, self._nchw(16, h2, w2),
+                                      feat, h2, w2, nhwc, OS=2, PY=py, PX=px)
+        return feat
+
+    # ------------------------------------------------------------------ IFBlock (IFNet_HDv3.py:84-96)
+    def _block(self, bi, img0, img1, f0, f1, timestep, ts_scalar, state, H, W, s):
+        name, cin, c = _BLOCKS[bi]
+        h, w = H // s, W // s
+        assert H % (4 * s) == 0 and W % (4 * s) == 0, "frame size must be a multiple of 4 * scale"
+        first = bi == 0
+        x = self._buf(("x", bi, H, W), (cin, h, w))
+        rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 0,
+                                        ptr(timestep), float(ts_scalar), None if first else ptr(state),
+                                        ptr(x), 0, 0, H, W, s, stream_ptr(self.device))
+        self._check(rc, "drba_ifnet_assemble")
+        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+        a = self._buf(("a", bi, H, W), (c // 2, h2, w2))
+        self._conv_direct(self.direct[f"{name}.conv0a"], ptr(x), h, w, self._nchw(cin, h, w), a, h2, w2, self._nchw(c // 2, h2, w2))
+        p0 = self._buf(("p0", bi, H, W), (c, h4, w4))
+        p1 = self._buf(("p1", bi, H, W), (c, h4, w4))
+        st4 = self._nchw(c, h4, w4)
+        self._conv_direct(self.direct[f"{name}.conv0b"], ptr(a), h2, w2, self._nchw(c // 2, h2, w2), p0, h4, w4, st4)
+        cur, nxt = p0, p1
+        for i in range(8):
+            self._conv_direct(self.direct[f"{name}.res{i}"], ptr(cur), h4, w4, st4, nxt, h4, w4, st4, res_ptr=ptr(cur))
+            cur, nxt = nxt, cur
+        ct = self._buf(("ct", bi, H, W), (52, h2, w2))
+        for py in (0, 1):
+            for px in (0, 1):
+                self._conv_direct(self.direct[f"{name}.last{py}{px}"], ptr(cur), h4, w4, st4, ct, h4, w4,
+                                  self._nchw(52, h2, w2), OS=2, PY=py, PX=px)
+        rc = self.L.drba_ifnet_upsample(ptr(ct), 0, ptr(state), 0 if first else 1, H, W, s, stream_ptr(self.device))
+        self._check(rc, "drba_ifnet_upsample")
+
+    @staticmethod
+    def _int_scale(s):
+        si = int(round(s))
+        if si < 1 or abs(si - s) > 1e-9 or (si & (si - 1)) != 0:
+            raise _lib.DrbaError(f"unsupported block scale {s}: the fused IFNet path needs power-of-two integer "
+                                 f"scales (scale <= 1.0 in RIFE(...))")
+        return si
+
+    # ------------------------------------------------------------------ IFNet.forward (IFNet_HDv3.py:126-177)
+    def forward(self, img0, img1, timestep, scale_list, f0=None, f1=None):
+        """img0, img1 [1,3,H,W] fp32; timestep float or [1,1,H,W] tensor; f0/f1 from encode().
+        Returns the interpolated frame [1,3,H,W] fp32 (merged[4] of the reference)."""
+        require_cuda(img0, img1)
+        img0, img1 = img0.float().contiguous(), img1.float().contiguous()
+        _, _, H, W = img0.shape
+        ts_t, ts_s = (timestep.float().contiguous(), 0.0) if torch.is_tensor(timestep) else (None, float(timestep))
+        with torch.cuda.device(self.device):
+            f0 = self.encode(img0) if f0 is None else f0
+            f1 = self.encode(img1) if f1 is None else f1
+            state = self._buf(("state", H, W), (H, W, 16))
+            for bi in range(5):
+                self._block(bi, img0, img1, f0, f1, ts_t, ts_s, state, H, W, self._int_scale(scale_list[bi]))
+            out = torch.empty((1, 3, H, W), dtype=torch.float32, device=self.device)
+            rc = self.L.drba_ifnet_blend(ptr(img0), ptr(img1), ptr(state), ptr(out), H, W, stream_ptr(self.device))
+            self._check(rc, "drba_ifnet_blend")
+        return out
+
+    def block0_flow(self, img0, img1, f0, f1, timestep, scale):
+        """ifnet.block0(cat(a, b, f0, f1, timestep), None, scale)[0] (models/rife.py:45-46): [1,4,H,W]."""
+        require_cuda(img0, img1)
+        img0, img1 = img0.float().contiguous(), img1.float().contiguous()
+        _, _, H, W = img0.shape
+        with torch.cuda.device(self.device):
+            state = self._buf(("state0", H, W), (H, W, 16))
+            self._block(0, img0, img1, f0, f1, None, float(timestep), state, H, W, self._int_scale(scale))
+            flow = torch.empty((1, 4, H, W), dtype=torch.float32, device=self.device)
+            rc = self.L.drba_ifnet_state_flow(ptr(state), ptr(flow), H, W, stream_ptr(self.device))
+            self._check(rc, "drba_ifnet_state_flow")
+        return flow

@@ -81,6 +81,7 @@ def find_rife_weights(explicit=None):
              "weights/train_log_rife_426_heavy",
              os.path.join(here, "weights/train_log_rife_426_heavy"),
              os.path.join(here, "oracle/_ref/weights/train_log_rife_426_heavy"),
+             os.path.join(here, "baseline/_ref/weights/train_log_rife_426_heavy"),
              "/root/reference/weights/train_log_rife_426_heavy"]
     for c in cands:
         if c and os.path.isfile(os.path.join(c, "flownet.pkl")):

@@ -123,6 +123,40 @@ DRBA_API int drba_backwarp_f32(const float* in, const float* flow, float* out,
 DRBA_API int drba_resize_bilinear_f32(const float* in, float* out, int N, int C, int H, int W,
                                       int OH, int OW, int align_corners, float rh, float rw, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * fp32 direct convolution (exact engine).  Generic form covering every conv on the
+ * IFNet path (models/rife_426_heavy/IFNet_HDv3.py:11-25 conv, :28-47 Head, :50-59 ResConv,
+ * :80 lastconv ConvTranspose2d(4,2,1) as four phase launches):
+ *   out[n,co,oy*OS+PY,ox*OS+PX] = act(bias[co] + res[same] + sum_t sum_ci in[n,ci,oy*S+dy[t],ox*S+dx[t]] * w[t][ci][co])
+ * in_strides / out_strides: element strides {n, c, y, x}; `res` (optional) is addressed
+ * like `out`.  w is packed [T][Cin][Cout] fp32.  act: 0 none, 1 LeakyReLU(0.2).
+ * ------------------------------------------------------------------------- */
+DRBA_API int drba_conv2d_direct_f32(const float* in, const float* w, const float* bias, const float* res, float* out,
+                                    int N, int Cin, int H, int W, const long long* in_strides,
+                                    int Cout, int OH, int OW, const long long* out_strides,
+                                    int S, int OS, int PY, int PX, int T, const int* dy, const int* dx,
+                                    int act, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Fused non-conv stages of IFNet.forward (IFNet_HDv3.py:126-177), batch 1.
+ * feature maps f0/f1: [H][W][16] (NHWC) of feat_dtype; state: [H][W][16] fp32 =
+ * {flow 4, mask 1, feat 8, pad 3}.
+ * drba_ifnet_assemble: conv input of one IFBlock at 1/s resolution (warp + cat + resize,
+ *   IFNet_HDv3.py:151-155 + :85-88).  state == NULL: first block (39 channels, no warp).
+ *   out_dtype DRBA_F32: NCHW [52|39][H/s][W/s]; DRBA_F16: NHWC [H/s][W/s][out_cstride].
+ * drba_ifnet_upsample: lastconv output -> x s bilinear -> state (IFNet_HDv3.py:91-96,:156-158).
+ *   tmp_layout 0: ConvT output NCHW fp32 [52][H/2s][W/2s]; 1: NHWC fp32 [H/s][W/s][16].
+ * drba_ifnet_blend: IFNet_HDv3.py:160-167.   drba_ifnet_state_flow: state -> [4][H][W].
+ * ------------------------------------------------------------------------- */
+DRBA_API int drba_ifnet_assemble(const float* img0, const float* img1, const void* f0, const void* f1, int feat_dtype,
+                                 const float* timestep, float timestep_scalar, const float* state,
+                                 void* out, int out_dtype, int out_cstride, int H, int W, int s, void* stream);
+DRBA_API int drba_ifnet_upsample(const float* tmp, int tmp_layout, float* state, int accumulate,
+                                 int H, int W, int s, void* stream);
+DRBA_API int drba_ifnet_blend(const float* img0, const float* img1, const float* state, float* out,
+                              int H, int W, void* stream);
+DRBA_API int drba_ifnet_state_flow(const float* state, float* flow, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
