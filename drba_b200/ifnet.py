@@ -67,6 +67,51 @@ def _pack_convT_phase(weight, py, px):
     return torch.stack(taps, 0), dy, dx
 
 
+class _TcLayer:
+    """One conv layer packed for drba_conv_tc_f16: w[G][T][cout_pad][cin_pad] fp16, bias[G][cout_pad] fp32."""
+
+    def __init__(self, w, b, dy, dx, stride, act, cout, epilogue, device):
+        self.w = w.to(torch.float16).contiguous().to(device)
+        self.b = b.float().contiguous().to(device)
+        self.G, self.T, self.cout_pad, self.cin = self.w.shape
+        self.cout = cout
+        self.dy = (ctypes.c_int * (self.G * self.T))(*dy)
+        self.dx = (ctypes.c_int * (self.G * self.T))(*dx)
+        self.stride = stride
+        self.act = act
+        self.epilogue = epilogue
+
+
+def _pad16(n):
+    return (n + 15) // 16 * 16
+
+
+def _tc_conv3x3(weight, bias, stride, act, device, beta=None):
+    w, b = _pack_conv3x3(weight, bias, beta)           # [9][Cin][Cout]
+    T, cin, cout = w.shape
+    wp = torch.zeros((1, T, _pad16(cout), _pad16(cin)))
+    wp[0, :, :cout, :cin] = w.permute(0, 2, 1)
+    bp = torch.zeros((1, _pad16(cout)))
+    bp[0, :cout] = b
+    dy, dx = _taps3x3()
+    return _TcLayer(wp, bp, dy, dx, stride, act, cout, 0, device)
+
+
+def _tc_lastconv(weight, bias, device):
+    cin, cout = weight.shape[0], weight.shape[1]       # [Cin, 52, 4, 4]
+    wp = torch.zeros((4, 4, 64, cin))
+    bp = torch.zeros((4, 64))
+    dys, dxs = [], []
+    for py in (0, 1):
+        for px in (0, 1):
+            w, dy, dx = _pack_convT_phase(weight, py, px)   # [4][Cin][Cout]
+            wp[py * 2 + px, :, :cout, :] = w.permute(0, 2, 1)
+            bp[py * 2 + px, :cout] = bias.float()
+            dys += dy
+            dxs += dx
+    return _TcLayer(wp, bp, dys, dxs, 1, 0, cout, 1, device)
+
+
 class IFNetEngine:
     def __init__(self, state, device, precision="fp32"):
         if precision not in ("fp32", "fp16"):
@@ -101,6 +146,15 @@ class IFNetEngine:
             for px in (0, 1):
                 w, dy, dx = _pack_convT_phase(sd["encode.cnn3.weight"], py, px)
                 self.direct[f"encode.cnn3.{py}{px}"] = _DirectLayer(w, sd["encode.cnn3.bias"], dy, dx, 1, 0, d)
+        self.tc = {}
+        if precision == "fp16":
+            for name, cin, c in _BLOCKS:
+                self.tc[f"{name}.conv0a"] = _tc_conv3x3(sd[f"{name}.conv0.0.0.weight"], sd[f"{name}.conv0.0.0.bias"], 2, 1, d)
+                self.tc[f"{name}.conv0b"] = _tc_conv3x3(sd[f"{name}.conv0.1.0.weight"], sd[f"{name}.conv0.1.0.bias"], 2, 1, d)
+                for i in range(8):
+                    p = f"{name}.convblock.{i}"
+                    self.tc[f"{name}.res{i}"] = _tc_conv3x3(sd[p + ".conv.weight"], sd[p + ".conv.bias"], 1, 1, d, sd[p + ".beta"])
+                self.tc[f"{name}.last"] = _tc_lastconv(sd[f"{name}.lastconv.0.weight"], sd[f"{name}.lastconv.0.bias"], d)
         self.launches = 0   # kernels launched through this engine (bench.py reports it)
 
     # ------------------------------------------------------------------ helpers
@@ -122,6 +176,12 @@ class IFNetEngine:
                                            layer.stride, OS, PY, PX, layer.T, layer.dy, layer.dx,
                                            layer.act, stream_ptr(self.device))
         self._check(rc, "drba_conv2d_direct_f32")
+
+    def _conv_tc(self, layer, x, H, W, out, OH, OW, out_cstride, res=None):
+        rc = self.L.drba_conv_tc_f16(ptr(x), H, W, layer.cin, ptr(layer.w), ptr(layer.b), layer.G, layer.T,
+                                     layer.dy, layer.dx, layer.cout_pad, layer.cout, layer.stride, OH, OW,
+                                     layer.epilogue, layer.act, ptr(res), ptr(out), out_cstride, stream_ptr(self.device))
+        self._check(rc, "drba_conv_tc_f16")
 
     @staticmethod
     def _nchw(c, h, w):
@@ -155,6 +215,8 @@ class IFNetEngine:
         h, w = H // s, W // s
         assert H % (4 * s) == 0 and W % (4 * s) == 0, "frame size must be a multiple of 4 * scale"
         first = bi == 0
+        if self.precision == "fp16":
+            return self._block_tc(bi, img0, img1, f0, f1, timestep, ts_scalar, state, H, W, s)
         x = self._buf(("x", bi, H, W), (cin, h, w))
         rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 0,
                                         ptr(timestep), float(ts_scalar), None if first else ptr(state),
@@ -177,6 +239,33 @@ class IFNetEngine:
                 self._conv_direct(self.direct[f"{name}.last{py}{px}"], ptr(cur), h4, w4, st4, ct, h4, w4,
                                   self._nchw(52, h2, w2), OS=2, PY=py, PX=px)
         rc = self.L.drba_ifnet_upsample(ptr(ct), 0, ptr(state), 0 if first else 1, H, W, s, stream_ptr(self.device))
+        self._check(rc, "drba_ifnet_upsample")
+
+    def _block_tc(self, bi, img0, img1, f0, f1, timestep, ts_scalar, state, H, W, s):
+        """Same schedule on the tensor-core engine: NHWC fp16 activations, 11 conv launches."""
+        name, cin, c = _BLOCKS[bi]
+        h, w = H // s, W // s
+        first = bi == 0
+        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+        cin_pad = _pad16(cin)
+        f16 = torch.float16
+        x = self._buf(("xh", bi, H, W), (h, w, cin_pad), f16)
+        rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 0 if f0.dtype == torch.float32 else 1,
+                                        ptr(timestep), float(ts_scalar), None if first else ptr(state),
+                                        ptr(x), 1, cin_pad, H, W, s, stream_ptr(self.device))
+        self._check(rc, "drba_ifnet_assemble")
+        a = self._buf(("ah", bi, H, W), (h2, w2, c // 2), f16)
+        self._conv_tc(self.tc[f"{name}.conv0a"], x, h, w, a, h2, w2, c // 2)
+        p0 = self._buf(("p0h", bi, H, W), (h4, w4, c), f16)
+        p1 = self._buf(("p1h", bi, H, W), (h4, w4, c), f16)
+        self._conv_tc(self.tc[f"{name}.conv0b"], a, h2, w2, p0, h4, w4, c)
+        cur, nxt = p0, p1
+        for i in range(8):
+            self._conv_tc(self.tc[f"{name}.res{i}"], cur, h4, w4, nxt, h4, w4, c, res=cur)
+            cur, nxt = nxt, cur
+        tmp = self._buf(("tmp13", bi, H, W), (h, w, 16), torch.float32)
+        self._conv_tc(self.tc[f"{name}.last"], cur, h4, w4, tmp, h4, w4, 16)
+        rc = self.L.drba_ifnet_upsample(ptr(tmp), 1, ptr(state), 0 if first else 1, H, W, s, stream_ptr(self.device))
         self._check(rc, "drba_ifnet_upsample")
 
     @staticmethod

@@ -138,6 +138,23 @@ DRBA_API int drba_conv2d_direct_f32(const float* in, const float* w, const float
                                     int act, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * tcgen05 implicit-GEMM convolution (tensor-core engine), fp16 operands, fp32 accumulate.
+ * Replaces the cuDNN fp16 convs the reference runs under torch.autocast for
+ * IFNet_HDv3.py:62-96 (conv0, ResConv x 8, lastconv).  Batch 1.
+ *   in   : NHWC fp16 [H][W][Cin], Cin % 16 == 0 (zero-padded channels)
+ *   w    : fp16 [G][T][cout_pad][Cin];  bias: fp32 [G][cout_pad];  dy, dx: int [G][T] tap offsets
+ *   out[oy][ox][co] = act(bias + res + sum_t sum_ci in[S*oy + dy[t]][S*ox + dx[t]][ci] * w[g][t][co][ci])
+ *   epilogue 0: NHWC fp16 [OH][OW][out_cstride] (G must be 1), optional residual `res` of the
+ *               same geometry, act 0 none / 1 LeakyReLU(0.2)
+ *   epilogue 1: lastconv = ConvTranspose2d(Cin,52,4,2,1)+PixelShuffle(2): G = 4 phases (py*2+px),
+ *               T = 4, cout_pad = 64, cout = 52; out = NHWC fp32 [4*OH][4*OW][16] (13 used)
+ * ------------------------------------------------------------------------- */
+DRBA_API int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
+                              const void* w, const float* bias, int G, int T, const int* dy, const int* dx,
+                              int cout_pad, int cout, int S, int OH, int OW,
+                              int epilogue, int act, const void* res, void* out, int out_cstride, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Fused non-conv stages of IFNet.forward (IFNet_HDv3.py:126-177), batch 1.
  * feature maps f0/f1: [H][W][16] (NHWC) of feat_dtype; state: [H][W][16] fp32 =
  * {flow 4, mask 1, feat 8, pad 3}.
