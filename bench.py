@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- DRBA hot path on B200: RIFE-4.26-heavy 1080p 24->60, scale 1.0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one sliding-triplet window of the reference's driver loop (infer.py:112-156):
+``RIFE.inference_ts_drba(I0, I1, I2, ts, reuse, linear=True)`` with the 24->60 timestamp schedule
+(windows alternate ts = [0.6, 1.0, 1.4] / [0.8, 1.2]: 2.5 output frames per window, 2 of them
+interpolated).  The metric is OUTPUT frames per second at net-input size 1088x1920.
+
+* value : whole-job frames/s with the frames already resident in HBM (CUDA events, K steps).
+* e2e   : the same through the public API with HOST buffers: every step copies the new frame
+          from pinned host memory to the device and every output frame back (fp32, like the
+          reference's to_inp / to_out, models/utils/tools.py:59-68).
+* roofline : the dominant kernel family of the step, timed live with CUDA events in an
+          instrumented pass of the same steps (drba_b200._lib.LaunchProfiler).
+* cpu_baseline : the oracle port of the reference path (oracle/ifnet.py, torch fp32 CPU convs +
+          C splat/warp) on the host cores, one window (rank 0, N = 1 only).
+* --impl reference : that CPU path as the reference arm (bounded number of windows).
+
+N > 1: frame-window sharding, one replica per GPU, no collective on the data path;
+every rank runs K windows of its own shard -> "scaling": "weak".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H_SRC, W_SRC = 1080, 1920
+METRIC = "output frames/s, RIFE-4.26-heavy 1080p 24->60 (DRBA inference_ts_drba windows)"
+UNIT = "frames/s"
+TS_PATTERN = [np.array([0.6, 1.0, 1.4]), np.array([0.8, 1.2])]   # calc_t() at 24 -> 60 fps (infer.py:76-91)
+
+
+def net_size(h, w, scale=1.0, div=64):
+    """get_valid_net_inp_size (models/utils/tools.py:41-56)."""
+    def up(v):
+        return int((v * scale // div + 1) * div / scale) if v * scale % div != 0 else v
+    return up(h), up(w)
+
+
+def synth_clip(n_frames, h, w, seed, device):
+    """Seeded low-frequency texture translated/warped smoothly from frame to frame."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    base = torch.rand((1, 3, h // 8 + 16, w // 8 + 16), generator=g)
+    base = torch.nn.functional.interpolate(base, scale_factor=8, mode="bicubic", align_corners=False).clamp(0, 1)
+    fine = torch.rand((1, 3, h + 128, w + 128), generator=g) * 0.15
+    tex = (base[:, :, : h + 128, : w + 128] * 0.85 + fine).to(device)
+    frames = []
+    for i in range(n_frames):
+        dx, dy = 5.5 * i, 2.25 * i
+        x0, y0 = int(dx), int(dy)
+        ax, ay = dx - x0, dy - y0
+        p = tex[:, :, y0:y0 + h + 1, x0:x0 + w + 1]
+        f = (p[:, :, :h, :w] * (1 - ax) * (1 - ay) + p[:, :, :h, 1:w + 1] * ax * (1 - ay)
+             + p[:, :, 1:h + 1, :w] * (1 - ax) * ay + p[:, :, 1:h + 1, 1:w + 1] * ax * ay)
+        frames.append(f.contiguous())
+    return frames
+
+
+def load_state():
+    from drba_b200.weights import find_rife_weights, load_ifnet_state, synth_ifnet_state
+    wdir = find_rife_weights()
+    if wdir is not None:
+        return load_ifnet_state(wdir), "reference checkpoint flownet.pkl"
+    return synth_ifnet_state(0), "seeded random-init weights (reference checkpoint not on this machine)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [int(r[1]) for r in self.rows if len(r) >= 7 and r[1].isdigit()]
+        mx = [int(r[2]) for r in self.rows if len(r) >= 7 and r[2].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return {"hbm": float(d.get("hbm_gbs", 6650.0)), "tensor": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))),
+                    "src": "MEASURED_PEAKS.json (sustained bf16; kernel timed inside a long step)"}
+        except Exception:
+            pass
+    return {"hbm": 6650.0, "tensor": 1590.0, "src": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_port_windows(h, w, n_windows, seed):
+    """The reference path restated on the CPU (oracle port): returns (seconds, output frames, threads)."""
+    from oracle.ifnet import RIFEOracle
+    state, _ = load_state()
+    torch.set_grad_enabled(False)
+    frames = synth_clip(n_windows + 2, h, w, seed, "cpu")
+    m = RIFEOracle(state)
+    reuse = None
+    # warm-up state like the sequential loop (first window computes both pairs); timed as part of the job
+    t0 = time.perf_counter()
+    nout = 0
+    for j in range(n_windows):
+        out, reuse = m.inference_ts_drba(frames[j], frames[j + 1], frames[j + 2], TS_PATTERN[j % 2], reuse, True)
+        nout += len(out)
+    return time.perf_counter() - t0, nout, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    h, w = net_size(H_SRC, W_SRC)
+    budget = 150.0
+    t1, n1, threads = cpu_port_windows(h, w, 1, 0)      # also the warm-up
+    k = max(1, min(args.steps, int(budget // max(t1, 1e-3))))
+    secs, nout, threads = cpu_port_windows(h, w, k, 0)
+    fps = nout / secs
+    line = {"impl": "reference", "metric": METRIC, "value": round(fps, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": k, "warmup": 1, "ms_per_step": round(1e3 * secs / k, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "RIFE-4.26-heavy 1080p 24->60, scale=1.0 (BASELINE.json configs[1]) on host CPU",
+                       "net_input": [h, w], "ts_pattern": "[0.6,1.0,1.4]/[0.8,1.2]"},
+            "cpu_baseline": {"value": round(fps, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{k} window(s) ({nout} output frames) of the same 1088x1920 clip; oracle port "
+                                       f"(torch fp32 CPU convs + C splat/warp); /root/reference cannot travel to the GPU box"},
+            "e2e": {"value": round(fps, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default=None, help="write the per-kernel-family breakdown here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from drba_b200 import _lib
+    from drba_b200.rife import RIFE
+    state, wdesc = load_state()
+    model = RIFE(state=state, device=dev, precision=args.precision)
+    h, w = net_size(H_SRC, W_SRC, model.scale, model.pad_size)
+    K, Wm = args.steps, args.warmup
+    ring = 8
+    frames = synth_clip(ring, h, w, 1000 + rank, dev)     # each rank: its own shard of the stream
+    host_frames = [f.cpu().pin_memory() for f in frames]
+    frame_bytes = frames[0].numel() * 4
+
+    def window(j, reuse, src):
+        return model.inference_ts_drba(src[j % ring], src[(j + 1) % ring], src[(j + 2) % ring], TS_PATTERN[j % 2], reuse, True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------
+    reuse = None
+    for j in range(Wm):
+        _, reuse = window(j, reuse, frames)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = _lib.KERNEL_LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nout = 0
+    ev0.record()
+    for j in range(Wm, Wm + K):
+        out, reuse = window(j, reuse, frames)
+        nout += len(out)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.KERNEL_LAUNCHES - launches0
+
+    # ---- end to end through the public API with host buffers -----------------------------------
+    out_host = [torch.empty((1, 3, h, w), dtype=torch.float32).pin_memory() for _ in range(3)]
+    dev_in = [torch.empty_like(frames[0]) for _ in range(3)]
+    for k in range(3):
+        dev_in[k].copy_(host_frames[k], non_blocking=True)
+    reuse_e = None
+    h2d = d2h = 0
+
+    def e2e_window(j, reuse_e, count):
+        nonlocal h2d, d2h
+        # the new frame of this window arrives from the host (to_inp); I0/I1 are carried over
+        slot = (j + 2) % 3
+        dev_in[slot].copy_(host_frames[(j + 2) % ring], non_blocking=True)
+        I0, I1, I2 = dev_in[j % 3], dev_in[(j + 1) % 3], dev_in[slot]
+        out, reuse_e = model.inference_ts_drba(I0, I1, I2, TS_PATTERN[j % 2], reuse_e, True)
+        for k, o in enumerate(out):
+            out_host[k].copy_(o, non_blocking=True)          # to_out: every output frame goes back
+        if count:
+            h2d += frame_bytes
+            d2h += frame_bytes * len(out)
+        return len(out), reuse_e
+
+    for j in range(Wm):
+        _, reuse_e = e2e_window(j, reuse_e, False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nout_e = 0
+    e0.record()
+    for j in range(Wm, Wm + K):
+        n, reuse_e = e2e_window(j, reuse_e, True)
+        nout_e += n
+    e1.record()
+    barrier()
+    ms_e = e0.elapsed_time(e1)
+    clk = clocks.stop()
+
+    # ---- instrumented pass: per-kernel-family shares and the roofline ------------------------------
+    with _lib.LaunchProfiler() as prof:
+        for j in range(Wm + K, Wm + K + min(K, 6)):
+            _, reuse = window(j, reuse, frames)
+        fam = prof.summary()
+    nprof = min(K, 6)
+
+    # ---- max over ranks -------------------------------------------------------------------------
+    t = torch.tensor([ms, ms_e], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(nout), float(nout_e)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, ms_e = float(t[0]), float(t[1])
+    nout_all, nout_e_all = float(tot[0]), float(tot[1])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        total_ms = sum(d["ms"] for d in fam.values()) or 1.0
+        top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        name, d = top
+        if d["flops"] > 0:
+            achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            roof = {"kernel": name, "bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["tensor"],
+                    "unit": "TFLOP/s", "frac": round(achieved / peaks["tensor"], 4), "traffic": None}
+        else:
+            achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["bytes"] else 0.0
+            roof = {"kernel": name, "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm"],
+                    "unit": "GB/s", "frac": round(achieved / peaks["hbm"], 4), "traffic": None}
+        roof.update({"launches_per_step": round(d["kernels"] / nprof, 1), "avg_launch_us": round(1e3 * d["ms"] / max(d["kernels"], 1), 2),
+                     "share_of_step": round(d["ms"] / total_ms, 3), "peak_source": peaks["src"]})
+        breakdown = {k: {"ms_per_step": round(v["ms"] / nprof, 4), "kernels_per_step": round(v["kernels"] / nprof, 1),
+                         "share": round(v["ms"] / total_ms, 3),
+                         "TFLOPs": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else None,
+                         "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] else None}
+                     for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+        if args.profile_json:
+            os.makedirs(os.path.dirname(os.path.abspath(args.profile_json)), exist_ok=True)
+            json.dump(breakdown, open(args.profile_json, "w"), indent=1)
+        print("per-kernel-family breakdown (instrumented pass): " + json.dumps(breakdown), file=sys.stderr)
+
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            secs, n_cpu, threads = cpu_port_windows(h, w, 1, 1000)
+            cpu = {"value": round(n_cpu / secs, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"1 window (ts=[0.6,1.0,1.4]: {n_cpu} output frames, cold start) of the same 1088x1920 clip, "
+                             f"{secs:.1f} s; oracle port (torch fp32 CPU convs + C splat/warp)"}
+        line = {"metric": METRIC, "value": round(nout_all / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world,
+                "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32",
+                "data": "synthetic",
+                "config": {"workload": "RIFE-4.26-heavy 1080p 24->60, scale=1.0 (BASELINE.json configs[1])",
+                           "net_input": [h, w], "ts_pattern": "[0.6,1.0,1.4]/[0.8,1.2] (2.5 output frames / window)",
+                           "weights": wdesc, "precision": args.precision + " convs (tcgen05), fp32 flow/DRM/warp/splat"
+                           if args.precision == "fp16" else "fp32",
+                           "parallelism": f"frame-window shards x{world}, no collective",
+                           "l2": "per-step working set (3 fp32 frames 75 MB + 134 MB state + features/activations) exceeds the 126 MB L2; ring of 8 distinct frames"},
+                "e2e": {"value": round(nout_e_all / (ms_e * 1e-3), 3), "unit": UNIT,
+                        "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K)},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,68 @@ def build(force=False, verbose=False):
 
 _lib = None
 
+# --- launch accounting ---------------------------------------------------------------
+# Every host wrapper reports the kernels it launched (count(), exact numbers) so bench.py can
+# state `gpu_launches`; with a LaunchProfiler installed each call is also bracketed by CUDA
+# events on the launching stream (per-kernel-family time shares and the roofline numbers).
+KERNEL_LAUNCHES = 0
+PROFILER = None
+
+
+def count(n):
+    global KERNEL_LAUNCHES
+    KERNEL_LAUNCHES += n
+
+
+class LaunchProfiler:
+    """Collects (family, ms, flops, bytes) per wrapped call; install with `with LaunchProfiler() as p:`."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global PROFILER
+        PROFILER = self
+        return self
+
+    def __exit__(self, *exc):
+        global PROFILER
+        PROFILER = None
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        fam = {}
+        for name, a, b, flops, nbytes, nk in self.records:
+            d = fam.setdefault(name, {"calls": 0, "kernels": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["calls"] += 1
+            d["kernels"] += nk
+            d["ms"] += a.elapsed_time(b)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return fam
+
+
+class launch:
+    """Context manager around one C-ABI call: counts its kernels, times it when profiling."""
+
+    def __init__(self, name, kernels=1, flops=0.0, nbytes=0.0):
+        self.name, self.kernels, self.flops, self.nbytes = name, kernels, flops, nbytes
+
+    def __enter__(self):
+        count(self.kernels)
+        if PROFILER is not None:
+            import torch
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILER is not None:
+            self.b.record()
+            PROFILER.records.append((self.name, self.a, self.b, self.flops, self.nbytes, self.kernels))
+
 
 def lib():
     """The loaded library; raises DrbaError when it has not been built."""

@@ -30,8 +30,9 @@ def get_drm_t(drm, t, precision=1e-3):
     x = f32c(drm)
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        rc = _lib.lib().drba_get_drm_t_f32(ptr(x), float(t), float(precision), ptr(out), x.numel(),
-                                           stream_ptr(x.device))
+        with _lib.launch("get_drm_t", 1, nbytes=8.0 * x.numel()):
+            rc = _lib.lib().drba_get_drm_t_f32(ptr(x), float(t), float(precision), ptr(out), x.numel(),
+                                               stream_ptr(x.device))
     _lib.check(rc, "drba_get_drm_t_f32")
     return out.to(dtype)
 
@@ -52,9 +53,11 @@ def _drm_rife(t, flow10, flow12, metric10, metric12, linear, only):
     with torch.cuda.device(f10.device):
         need = L.drba_drm_workspace_bytes(n, h, w)
         ws = Workspace.get(need, f10.device)
-        rc = L.drba_drm_rife_f32(float(t), ptr(f10), ptr(f12), ptr(m10), ptr(m12), int(bool(linear)),
-                                 ptr(outs[names[0]]), ptr(outs[names[1]]), n, h, w,
-                                 ws.data_ptr(), need, stream_ptr(f10.device))
+        nmaps = sum(v is not None for v in outs.values())
+        with _lib.launch("drm_rife", 2, nbytes=float(n * h * w * (16 + (8 if soft else 0) + 4 * nmaps))):
+            rc = L.drba_drm_rife_f32(float(t), ptr(f10), ptr(f12), ptr(m10), ptr(m12), int(bool(linear)),
+                                     ptr(outs[names[0]]), ptr(outs[names[1]]), n, h, w,
+                                     ws.data_ptr(), need, stream_ptr(f10.device))
     _lib.check(rc, "drba_drm_rife_f32")
     return {k: v.to(dtype) for k, v in outs.items() if v is not None}
 
@@ -81,7 +84,8 @@ def calc_drm_gmfss(t, flow10, flow12, metric10, metric12, linear=False):
     with torch.cuda.device(f10.device):
         need = L.drba_drm_workspace_bytes(n, h, w)
         ws = Workspace.get(need, f10.device)
-        rc = L.drba_drm_gmfss_f32(float(t), ptr(f10), ptr(f12), ptr(m10), ptr(m12), int(bool(linear)),
-                                  *[ptr(o) for o in outs], n, h, w, ws.data_ptr(), need, stream_ptr(f10.device))
+        with _lib.launch("drm_gmfss", 3, nbytes=float(n * h * w * (16 + (8 if soft else 0) + 16))):
+            rc = L.drba_drm_gmfss_f32(float(t), ptr(f10), ptr(f12), ptr(m10), ptr(m12), int(bool(linear)),
+                                      *[ptr(o) for o in outs], n, h, w, ws.data_ptr(), need, stream_ptr(f10.device))
     _lib.check(rc, "drba_drm_gmfss_f32")
     return {k: v.to(dtype) for k, v in zip(names, outs)}

@@ -70,7 +70,8 @@ def _pack_convT_phase(weight, py, px):
 class _TcLayer:
     """One conv layer packed for drba_conv_tc_f16: w[G][T][cout_pad][cin_pad] fp16, bias[G][cout_pad] fp32."""
 
-    def __init__(self, w, b, dy, dx, stride, act, cout, epilogue, device):
+    def __init__(self, w, b, dy, dx, stride, act, cout, epilogue, device, cin_real=None):
+        self.cin_real = cin_real if cin_real is not None else w.shape[3]
         self.w = w.to(torch.float16).contiguous().to(device)
         self.b = b.float().contiguous().to(device)
         self.G, self.T, self.cout_pad, self.cin = self.w.shape
@@ -94,7 +95,7 @@ def _tc_conv3x3(weight, bias, stride, act, device, beta=None):
     bp = torch.zeros((1, _pad16(cout)))
     bp[0, :cout] = b
     dy, dx = _taps3x3()
-    return _TcLayer(wp, bp, dy, dx, stride, act, cout, 0, device)
+    return _TcLayer(wp, bp, dy, dx, stride, act, cout, 0, device, cin_real=cin)
 
 
 def _tc_lastconv(weight, bias, device):
@@ -169,18 +170,25 @@ class IFNetEngine:
         self.launches += 1
         _lib.check(rc, what)
 
+    @staticmethod
+    def _launch(name, flops=0.0, nbytes=0.0):
+        return _lib.launch(name, 1, flops, nbytes)
+
     def _conv_direct(self, layer, x_ptr, H, W, in_strides, out_t, OH, OW, out_strides, OS=1, PY=0, PX=0, res_ptr=None):
-        rc = self.L.drba_conv2d_direct_f32(x_ptr, ptr(layer.w), ptr(layer.b), res_ptr, ptr(out_t),
-                                           1, layer.cin, H, W, _LL4(*in_strides),
-                                           layer.cout, OH, OW, _LL4(*out_strides),
-                                           layer.stride, OS, PY, PX, layer.T, layer.dy, layer.dx,
-                                           layer.act, stream_ptr(self.device))
+        with self._launch("conv_direct_f32", flops=2.0 * layer.T * layer.cin * layer.cout * OH * OW):
+            rc = self.L.drba_conv2d_direct_f32(x_ptr, ptr(layer.w), ptr(layer.b), res_ptr, ptr(out_t),
+                                               1, layer.cin, H, W, _LL4(*in_strides),
+                                               layer.cout, OH, OW, _LL4(*out_strides),
+                                               layer.stride, OS, PY, PX, layer.T, layer.dy, layer.dx,
+                                               layer.act, stream_ptr(self.device))
         self._check(rc, "drba_conv2d_direct_f32")
 
     def _conv_tc(self, layer, x, H, W, out, OH, OW, out_cstride, res=None):
-        rc = self.L.drba_conv_tc_f16(ptr(x), H, W, layer.cin, ptr(layer.w), ptr(layer.b), layer.G, layer.T,
-                                     layer.dy, layer.dx, layer.cout_pad, layer.cout, layer.stride, OH, OW,
-                                     layer.epilogue, layer.act, ptr(res), ptr(out), out_cstride, stream_ptr(self.device))
+        # algorithmic FLOPs: real channels only (2 * Cin * Cout * taps * Hout * Wout)
+        with self._launch("conv_tc_f16", flops=2.0 * layer.G * layer.T * layer.cin_real * layer.cout * OH * OW):
+            rc = self.L.drba_conv_tc_f16(ptr(x), H, W, layer.cin, ptr(layer.w), ptr(layer.b), layer.G, layer.T,
+                                         layer.dy, layer.dx, layer.cout_pad, layer.cout, layer.stride, OH, OW,
+                                         layer.epilogue, layer.act, ptr(res), ptr(out), out_cstride, stream_ptr(self.device))
         self._check(rc, "drba_conv_tc_f16")
 
     @staticmethod
@@ -218,9 +226,10 @@ class IFNetEngine:
         if self.precision == "fp16":
             return self._block_tc(bi, img0, img1, f0, f1, timestep, ts_scalar, state, H, W, s)
         x = self._buf(("x", bi, H, W), (cin, h, w))
-        rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 0,
-                                        ptr(timestep), float(ts_scalar), None if first else ptr(state),
-                                        ptr(x), 0, 0, H, W, s, stream_ptr(self.device))
+        with self._launch("ifnet_assemble"):
+            rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 0,
+                                            ptr(timestep), float(ts_scalar), None if first else ptr(state),
+                                            ptr(x), 0, 0, H, W, s, stream_ptr(self.device))
         self._check(rc, "drba_ifnet_assemble")
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
         a = self._buf(("a", bi, H, W), (c // 2, h2, w2))
@@ -238,7 +247,8 @@ class IFNetEngine:
             for px in (0, 1):
                 self._conv_direct(self.direct[f"{name}.last{py}{px}"], ptr(cur), h4, w4, st4, ct, h4, w4,
                                   self._nchw(52, h2, w2), OS=2, PY=py, PX=px)
-        rc = self.L.drba_ifnet_upsample(ptr(ct), 0, ptr(state), 0 if first else 1, H, W, s, stream_ptr(self.device))
+        with self._launch("ifnet_upsample"):
+            rc = self.L.drba_ifnet_upsample(ptr(ct), 0, ptr(state), 0 if first else 1, H, W, s, stream_ptr(self.device))
         self._check(rc, "drba_ifnet_upsample")
 
     def _block_tc(self, bi, img0, img1, f0, f1, timestep, ts_scalar, state, H, W, s):
@@ -250,9 +260,10 @@ class IFNetEngine:
         cin_pad = _pad16(cin)
         f16 = torch.float16
         x = self._buf(("xh", bi, H, W), (h, w, cin_pad), f16)
-        rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 0 if f0.dtype == torch.float32 else 1,
-                                        ptr(timestep), float(ts_scalar), None if first else ptr(state),
-                                        ptr(x), 1, cin_pad, H, W, s, stream_ptr(self.device))
+        with self._launch("ifnet_assemble"):
+            rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 0 if f0.dtype == torch.float32 else 1,
+                                            ptr(timestep), float(ts_scalar), None if first else ptr(state),
+                                            ptr(x), 1, cin_pad, H, W, s, stream_ptr(self.device))
         self._check(rc, "drba_ifnet_assemble")
         a = self._buf(("ah", bi, H, W), (h2, w2, c // 2), f16)
         self._conv_tc(self.tc[f"{name}.conv0a"], x, h, w, a, h2, w2, c // 2)
@@ -265,7 +276,8 @@ class IFNetEngine:
             cur, nxt = nxt, cur
         tmp = self._buf(("tmp13", bi, H, W), (h, w, 16), torch.float32)
         self._conv_tc(self.tc[f"{name}.last"], cur, h4, w4, tmp, h4, w4, 16)
-        rc = self.L.drba_ifnet_upsample(ptr(tmp), 1, ptr(state), 0 if first else 1, H, W, s, stream_ptr(self.device))
+        with self._launch("ifnet_upsample"):
+            rc = self.L.drba_ifnet_upsample(ptr(tmp), 1, ptr(state), 0 if first else 1, H, W, s, stream_ptr(self.device))
         self._check(rc, "drba_ifnet_upsample")
 
     @staticmethod
@@ -291,7 +303,8 @@ class IFNetEngine:
             for bi in range(5):
                 self._block(bi, img0, img1, f0, f1, ts_t, ts_s, state, H, W, self._int_scale(scale_list[bi]))
             out = torch.empty((1, 3, H, W), dtype=torch.float32, device=self.device)
-            rc = self.L.drba_ifnet_blend(ptr(img0), ptr(img1), ptr(state), ptr(out), H, W, stream_ptr(self.device))
+            with self._launch("ifnet_blend"):
+                rc = self.L.drba_ifnet_blend(ptr(img0), ptr(img1), ptr(state), ptr(out), H, W, stream_ptr(self.device))
             self._check(rc, "drba_ifnet_blend")
         return out
 
@@ -304,6 +317,7 @@ class IFNetEngine:
             state = self._buf(("state0", H, W), (H, W, 16))
             self._block(0, img0, img1, f0, f1, None, float(timestep), state, H, W, self._int_scale(scale))
             flow = torch.empty((1, 4, H, W), dtype=torch.float32, device=self.device)
-            rc = self.L.drba_ifnet_state_flow(ptr(state), ptr(flow), H, W, stream_ptr(self.device))
+            with self._launch("ifnet_state_flow"):
+                rc = self.L.drba_ifnet_state_flow(ptr(state), ptr(flow), H, W, stream_ptr(self.device))
             self._check(rc, "drba_ifnet_state_flow")
         return flow

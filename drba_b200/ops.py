@@ -15,8 +15,9 @@ def backwarp(tenInput, tenFlow, padding_mode="border"):
     assert f.shape == (n, 2, h, w)
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        rc = _lib.lib().drba_backwarp_f32(ptr(x), ptr(f), ptr(out), n, c, h, w,
-                                          {"border": 0, "zeros": 1}[padding_mode], stream_ptr(x.device))
+        with _lib.launch("backwarp", 1, nbytes=4.0 * n * h * w * (2 * c + 2)):
+            rc = _lib.lib().drba_backwarp_f32(ptr(x), ptr(f), ptr(out), n, c, h, w,
+                                              {"border": 0, "zeros": 1}[padding_mode], stream_ptr(x.device))
     _lib.check(rc, "drba_backwarp_f32")
     return out.to(dtype)
 
@@ -35,8 +36,9 @@ def resize_bilinear(x, size=None, scale_factor=None, align_corners=False):
         rh = rw = 1.0 / scale_factor
     out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=xf.device)
     with torch.cuda.device(xf.device):
-        rc = _lib.lib().drba_resize_bilinear_f32(ptr(xf), ptr(out), n, c, h, w, oh, ow,
-                                                 int(bool(align_corners)), rh, rw, stream_ptr(xf.device))
+        with _lib.launch("resize_bilinear", 1, nbytes=4.0 * n * c * (h * w + oh * ow)):
+            rc = _lib.lib().drba_resize_bilinear_f32(ptr(xf), ptr(out), n, c, h, w, oh, ow,
+                                                     int(bool(align_corners)), rh, rw, stream_ptr(xf.device))
     _lib.check(rc, "drba_resize_bilinear_f32")
     return out.to(dtype)
 
@@ -51,6 +53,7 @@ def rife_invert_flow(flow_t0):
     with torch.cuda.device(f.device):
         need = L.drba_rife_invert_flow_workspace_bytes(n, h, w)
         ws = Workspace.get(need, f.device)
-        rc = L.drba_rife_invert_flow_f32(ptr(f), ptr(out), n, h, w, ws.data_ptr(), need, stream_ptr(f.device))
+        with _lib.launch("rife_invert_flow", 2, nbytes=16.0 * n * h * w):
+            rc = L.drba_rife_invert_flow_f32(ptr(f), ptr(out), n, h, w, ws.data_ptr(), need, stream_ptr(f.device))
     _lib.check(rc, "drba_rife_invert_flow_f32")
     return out

@@ -50,8 +50,14 @@ def softsplat(tenIn, tenFlow, tenMetric, strMode: str, _variant=0):
     with torch.cuda.device(x.device):
         need = L.drba_softsplat_workspace_bytes(n, c, h, w, mode)
         ws = Workspace.get(need, x.device)
-        rc = L.drba_softsplat_f32_variant(ptr(x), ptr(flow), ptr(metric), ptr(out), n, c, h, w, mode, eps,
-                                          ws.data_ptr(), need, int(_variant), stream_ptr(x.device))
+        group_bytes = n * h * w * 16
+        has_w = 0 if mode == 0 else 1
+        cc_max = max(1, (need // group_bytes) * 4 - has_w) if group_bytes else 1
+        chunks = max(1, -(-c // cc_max))
+        with _lib.launch("softsplat", 2 * chunks,
+                         nbytes=4.0 * n * h * w * ((c + 2 + (1 if metric is not None else 0)) + c)):
+            rc = L.drba_softsplat_f32_variant(ptr(x), ptr(flow), ptr(metric), ptr(out), n, c, h, w, mode, eps,
+                                              ws.data_ptr(), need, int(_variant), stream_ptr(x.device))
     _lib.check(rc, "drba_softsplat_f32")
     return out.to(output_dtype)
 

@@ -110,7 +110,23 @@ def backwarp(ten_in, flow, padding="border"):
     x, f = _f32(ten_in), _f32(flow)
     n, c, h, w = x.shape
     out = np.empty_like(x)
-    lib().orc_backwarp(_p(x), _p(f), _p(out), n, c, h, w, 0 if padding == "border" else 1)
+    pad = 0 if padding == "border" else 1
+    nthr = min(c, os.cpu_count() or 1)
+    if n != 1 or nthr < 2 or h * w < 65536:
+        lib().orc_backwarp(_p(x), _p(f), _p(out), n, c, h, w, pad)
+        return out
+    # channels are independent: run channel slices on host threads (ctypes drops the GIL);
+    # the arithmetic per element is unchanged
+    from concurrent.futures import ThreadPoolExecutor
+    L = lib()
+    bounds = np.linspace(0, c, nthr + 1).astype(int)
+
+    def run(i):
+        a, b = int(bounds[i]), int(bounds[i + 1])
+        if b > a:
+            L.orc_backwarp(_p(x[:, a:b]), _p(f), _p(out[:, a:b]), 1, b - a, h, w, pad)
+    with ThreadPoolExecutor(nthr) as ex:
+        list(ex.map(run, range(nthr)))
     return out
 
 
