@@ -36,6 +36,7 @@ struct DirectConvParams {
     int dy[kMaxTaps], dx[kMaxTaps];
     int min_dy, min_dx, PH, PW;       // staged patch geometry
     int act;                          // 0 none, 1 LeakyReLU(0.2)
+    int out_half;                     // store fp16 instead of fp32 (res, if any, is then fp16 too)
 };
 
 __global__ void __launch_bounds__(kTile * kTile)
@@ -104,9 +105,10 @@ direct_conv_kernel(const DirectConvParams p)
         const int co = co0 + k;
         if (co >= p.Cout) break;
         float v = acc[k] + (p.bias ? p.bias[co] : 0.0f);
-        if (p.res) v += p.res[o + co * p.out_sc];
+        if (p.res) v += p.out_half ? __half2float(reinterpret_cast<const __half*>(p.res)[o + co * p.out_sc]) : p.res[o + co * p.out_sc];
         if (p.act == 1) v = v > 0.0f ? v : 0.2f * v;
-        p.out[o + co * p.out_sc] = v;
+        if (p.out_half) reinterpret_cast<__half*>(p.out)[o + co * p.out_sc] = __float2half_rn(v);
+        else p.out[o + co * p.out_sc] = v;
     }
 }
 
@@ -116,7 +118,7 @@ using namespace drba;
 
 extern "C" {
 
-int drba_conv2d_direct_f32(const float* in, const float* w, const float* bias, const float* res, float* out,
+int drba_conv2d_direct_f32(const float* in, const float* w, const float* bias, const void* res, void* out, int out_dtype,
                            int N, int Cin, int H, int W, const long long* in_strides,
                            int Cout, int OH, int OW, const long long* out_strides,
                            int S, int OS, int PY, int PX, int T, const int* dy, const int* dx,
@@ -125,10 +127,11 @@ int drba_conv2d_direct_f32(const float* in, const float* w, const float* bias, c
     if (N < 0 || Cin <= 0 || H <= 0 || W <= 0 || Cout <= 0 || OH < 0 || OW < 0) return DRBA_E_ARG;
     if (T <= 0 || T > kMaxTaps || S <= 0 || OS <= 0 || !dy || !dx || !in_strides || !out_strides) return DRBA_E_ARG;
     if (act != 0 && act != 1) return DRBA_E_ARG;
+    if (out_dtype != DRBA_F32 && out_dtype != DRBA_F16) return DRBA_E_ARG;
     if ((size_t)N * OH * OW == 0) return DRBA_OK;
     if (!in || !w || !out) return DRBA_E_ARG;
     DirectConvParams p;
-    p.in = in; p.w = w; p.bias = bias; p.res = res; p.out = out;
+    p.in = in; p.w = w; p.bias = bias; p.res = (const float*)res; p.out = (float*)out; p.out_half = out_dtype == DRBA_F16;
     p.N = N; p.Cin = Cin; p.H = H; p.W = W;
     p.in_sn = in_strides[0]; p.in_sc = in_strides[1]; p.in_sy = in_strides[2]; p.in_sx = in_strides[3];
     p.Cout = Cout; p.OH = OH; p.OW = OW;

@@ -15,10 +15,13 @@
 //                   exist.  Output: channels [warp(img0) 3 | warp(img1) 3 | warp(f0) 16 |
 //                   warp(f1) 16 | timestep 1 | mask 1 | feat 8 | flow/s 4] (IFNet_HDv3.py:151-
 //                   155 + :87-88), NCHW fp32 (exact engine) or NHWC fp16 (tensor-core engine).
-//  ifnet_upsample : lastconv output (13 ch at 1/s) -> bilinear x s -> flow(+=) * s, mask, feat
-//                   (IFNet_HDv3.py:91-96, :156-158) into the full-resolution state tensor
-//                   [H][W][16] fp32 = {flow 4, mask 1, feat 8, pad 3}.
-//  ifnet_blend    : final warps + sigmoid blend (IFNet_HDv3.py:162-167).
+//                   Four threads per output pixel (f0 | f1 | images | timestep,mask,feat,flow);
+//                   mask/feat are bilinear taps of the previous block's small lastconv output
+//                   (L2 resident) -- a full-resolution mask/feat tensor is never written.
+//  ifnet_flow_accum: the only full-resolution state is the fp32 flow [H][W][4]:
+//                   flow (+)= s * up(lastconv[0:4])  (IFNet_HDv3.py:91-93, :157), 32 B/px.
+//  ifnet_blend    : last flow update + final warps + sigmoid blend (IFNet_HDv3.py:156-167) in
+//                   one pass; the last block's flow/mask are never stored at full resolution.
 #include "common.cuh"
 
 namespace drba {
@@ -104,184 +107,263 @@ __device__ __forceinline__ void sample_feat16(const FT* __restrict__ f, const Wa
         for (int c = 0; c < 16; ++c) out[c] += v[c] * t.w11; }
 }
 
+// ---- lastconv output access -----------------------------------------------------------
+// TMP_LAYOUT 0: ConvTranspose output, NCHW fp32 [52][h13/2][w13/2] (PixelShuffle(2) is index
+//               arithmetic here: IFNet_HDv3.py:81)
+// TMP_LAYOUT 1: pixel-shuffled NHWC fp32 [h13][w13][16] (13 used), written by the tensor-core
+//               engine's lastconv epilogue
+struct Tmp13 {
+    const float* p; int h13, w13, s;   // 13-channel map at 1/s of the full resolution
+};
+
+struct Bilin {           // F.interpolate(scale_factor=s, bilinear, align_corners=False) source taps
+    int y0, y1, x0, x1;
+    float ly, hy, lx, hx;
+};
+
+__device__ __forceinline__ Bilin bilin_up(int y, int x, const Tmp13& t)
+{
+    Bilin b;
+    const float r = 1.0f / (float)t.s;                 // ATen: ratio = 1 / scale_factor
+    float sy = r * ((float)y + 0.5f) - 0.5f, sx = r * ((float)x + 0.5f) - 0.5f;
+    if (sy < 0.0f) sy = 0.0f;
+    if (sx < 0.0f) sx = 0.0f;
+    b.y0 = (int)sy; b.x0 = (int)sx;
+    b.y1 = b.y0 + (b.y0 < t.h13 - 1 ? 1 : 0);
+    b.x1 = b.x0 + (b.x0 < t.w13 - 1 ? 1 : 0);
+    b.ly = sy - (float)b.y0; b.hy = 1.0f - b.ly;
+    b.lx = sx - (float)b.x0; b.hx = 1.0f - b.lx;
+    return b;
+}
+
+template <int TMP_LAYOUT, int C0, int NC>
+__device__ __forceinline__ void load_tmp(const Tmp13& t, int yy, int xx, float* v)
+{
+    if (TMP_LAYOUT == 0) {
+        const int h2 = t.h13 >> 1, w2 = t.w13 >> 1;
+        const size_t base = (size_t)(yy >> 1) * w2 + (xx >> 1);
+        const int sub = (yy & 1) * 2 + (xx & 1);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v[c] = t.p[(size_t)((C0 + c) * 4 + sub) * h2 * w2 + base];
+    } else {
+        const float* q = t.p + ((size_t)yy * t.w13 + xx) * 16;
+        if (C0 % 4 == 0) {
+            const float4* q4 = reinterpret_cast<const float4*>(q + C0);
+#pragma unroll
+            for (int c4 = 0; c4 < (NC + 3) / 4; ++c4) {
+                const float4 a = q4[c4];
+                if (c4 * 4 + 0 < NC) v[c4 * 4 + 0] = a.x;
+                if (c4 * 4 + 1 < NC) v[c4 * 4 + 1] = a.y;
+                if (c4 * 4 + 2 < NC) v[c4 * 4 + 2] = a.z;
+                if (c4 * 4 + 3 < NC) v[c4 * 4 + 3] = a.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) v[c] = q[C0 + c];
+        }
+    }
+}
+
+// channels [C0, C0+NC) of the x s bilinear up-sampling of the 13-channel map at (y, x)
+template <int TMP_LAYOUT, int C0, int NC>
+__device__ __forceinline__ void up_tmp(const Tmp13& t, int y, int x, float* o)
+{
+    const Bilin b = bilin_up(y, x, t);
+    float a[NC], bb[NC], c[NC], d[NC];
+    load_tmp<TMP_LAYOUT, C0, NC>(t, b.y0, b.x0, a);
+    load_tmp<TMP_LAYOUT, C0, NC>(t, b.y0, b.x1, bb);
+    load_tmp<TMP_LAYOUT, C0, NC>(t, b.y1, b.x0, c);
+    load_tmp<TMP_LAYOUT, C0, NC>(t, b.y1, b.x1, d);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) o[k] = b.hy * (b.hx * a[k] + b.lx * bb[k]) + b.ly * (b.hx * c[k] + b.lx * d[k]);
+}
+
+// ---- flow state: flow (+)= s * up(tmp[0:4])  (IFNet_HDv3.py:91-93, :157) ---------------------
+template <int TMP_LAYOUT>
+__global__ void __launch_bounds__(256)
+ifnet_flow_accum_kernel(const Tmp13 t, float* __restrict__ flow, float* __restrict__ planar, int accumulate, int H, int W)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= H * W) return;
+    const int y = idx / W, x = idx - y * W;
+    float o[4];
+    up_tmp<TMP_LAYOUT, 0, 4>(t, y, x, o);
+    const float fs = (float)t.s;
+    float4 f = make_float4(o[0] * fs, o[1] * fs, o[2] * fs, o[3] * fs);
+    float4* dst = reinterpret_cast<float4*>(flow) + idx;
+    if (accumulate) {
+        const float4 old = *dst;
+        f.x = old.x + f.x; f.y = old.y + f.y; f.z = old.z + f.z; f.w = old.w + f.w;
+    }
+    if (flow) *dst = f;
+    if (planar) {
+        const size_t HW = (size_t)H * W;
+        planar[idx] = f.x; planar[HW + idx] = f.y; planar[2 * HW + idx] = f.z; planar[3 * HW + idx] = f.w;
+    }
+}
+
+// ---- block input assembly ---------------------------------------------------------------
 struct AssembleParams {
     const float* img0; const float* img1;   // [3][H][W] fp32
     const void* f0; const void* f1;         // [H][W][16] FT
     const float* timestep; float timestep_scalar;   // [H][W] or NULL -> scalar
-    const float* state;                     // [H][W][16] fp32 or NULL (first block: no warp, 39 channels)
-    void* out; int out_cstride;             // NHWC: channels allocated per pixel (>= 52/39, rest zero-filled)
+    const float* flow;                      // [H][W][4] fp32 state, or NULL (first block: no warp, 39 channels)
+    Tmp13 prev;                             // previous block's lastconv output (mask/feat source)
+    void* out; int out_cstride;             // NHWC: channels allocated per pixel
     int H, W, s, h, w;                      // full size, integer scale, h = H/s, w = W/s
 };
 
+// Mean of the (up to) 4 sampled positions in the order bilinear resampling adds them:
+// 0.5*(0.5*a + 0.5*b) + 0.5*(0.5*c + 0.5*d) == ((a + b) + (c + d)) * 0.25 exactly in fp32.
+// a0 collects positions 0,1 (top row), a1 positions 2,3 (bottom row).
+template <int K>
+__device__ __forceinline__ void acc_pos(float& a0, float& a1, float val)
+{
+    if (K == 0) a0 = val;
+    else if (K == 1) a0 += val;
+    else if (K == 2) a1 = val;
+    else a1 += val;
+}
+__device__ __forceinline__ float mean_pos(float a0, float a1, int np) { return np == 1 ? a0 : (a0 + a1) * 0.25f; }
+
+// Output channel of (role, k).  Reference order (IFNet_HDv3.py:151-155 + :88):
+//   [warp(img0) 0-2 | warp(img1) 3-5 | warp(f0) 6-21 | warp(f1) 22-37 | timestep 38 | mask 39 | feat 40-47 | flow 48-51]
+// NHWC fp16 (tensor-core engine) uses a packed order of four aligned 16-channel segments, one per
+// role, so each thread stores 32 contiguous bytes; the host permutes the conv weights to match:
+//   [f0 16 | f1 16 | img0 3, img1 3, (first block: timestep), pad | timestep, mask, feat 8, flow 4, pad 2]
+__device__ __forceinline__ int ref_channel(int role, int k)
+{
+    return role == 0 ? 6 + k : (role == 1 ? 22 + k : (role == 2 ? (k < 6 ? k : 38) : 38 + k));
+}
+
 template <bool NHWC_HALF>
-__device__ __forceinline__ void store_channels(const AssembleParams& p, int Y, int X, int c0, const float* v, int n)
+__device__ __forceinline__ void store16(const AssembleParams& p, int Y, int X, int role, const float* v, int n)
 {
     if (NHWC_HALF) {
-        __half* o = reinterpret_cast<__half*>(p.out) + ((size_t)Y * p.w + X) * p.out_cstride + c0;
-        for (int c = 0; c < n; ++c) o[c] = __float2half_rn(v[c]);
+        uint4 o[2];
+        __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) oh[k] = __floats2half2_rn(2 * k < n ? v[2 * k] : 0.0f, 2 * k + 1 < n ? v[2 * k + 1] : 0.0f);
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + ((size_t)Y * p.w + X) * p.out_cstride + role * 16);
+        dst[0] = o[0]; dst[1] = o[1];
     } else {
-        float* o = reinterpret_cast<float*>(p.out) + (size_t)c0 * p.h * p.w + (size_t)Y * p.w + X;
-        for (int c = 0; c < n; ++c) o[(size_t)c * p.h * p.w] = v[c];
+        float* o = reinterpret_cast<float*>(p.out) + (size_t)Y * p.w + X;
+        const size_t hw = (size_t)p.h * p.w;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < n) o[(size_t)ref_channel(role, k) * hw] = v[k];
     }
 }
 
-// mean of the (up to) 4 sampled positions in the order bilinear resampling adds them:
-// 0.5*(0.5*a + 0.5*b) + 0.5*(0.5*c + 0.5*d) == ((a + b) + (c + d)) * 0.25 exactly in fp32
-__device__ __forceinline__ float mean4(const float* q, int np)
+template <typename FT, int K>
+__device__ __forceinline__ void feat_pos(const AssembleParams& p, const FT* f, int role, int x, int y, const float4& fl,
+                                         float* a0, float* a1)
 {
-    return np == 1 ? q[0] : ((q[0] + q[1]) + (q[2] + q[3])) * 0.25f;
+    // f0 follows flow[:2], f1 follows flow[2:4] (IFNet_HDv3.py:152-153)
+    const WarpTap t = warp_tap(x, y, role == 0 ? fl.x : fl.z, role == 0 ? fl.y : fl.w, p.H, p.W);
+    float q[16];
+    sample_feat16<FT>(f, t, q);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc_pos<K>(a0[c], a1[c], q[c]);
 }
 
-template <typename FT, bool NHWC_HALF>
+template <int K>
+__device__ __forceinline__ void img_pos(const AssembleParams& p, int x, int y, const float4& fl, size_t HW, float* a0, float* a1)
+{
+    const WarpTap t0 = warp_tap(x, y, fl.x, fl.y, p.H, p.W);
+    const WarpTap t1 = warp_tap(x, y, fl.z, fl.w, p.H, p.W);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        acc_pos<K>(a0[c], a1[c], sample_plane(p.img0 + (size_t)c * HW, t0));
+        acc_pos<K>(a0[3 + c], a1[3 + c], sample_plane(p.img1 + (size_t)c * HW, t1));
+    }
+    acc_pos<K>(a0[6], a1[6], p.timestep ? p.timestep[(size_t)y * p.W + x] : p.timestep_scalar);
+}
+
+template <int TMP_LAYOUT, int K>
+__device__ __forceinline__ void misc_pos(const AssembleParams& p, int x, int y, const float4& fl, float* a0, float* a1)
+{
+    acc_pos<K>(a0[0], a1[0], p.timestep ? p.timestep[(size_t)y * p.W + x] : p.timestep_scalar);
+    float mf[9];
+    up_tmp<TMP_LAYOUT, 4, 9>(p.prev, y, x, mf);     // mask, feat: x s_prev up-sampling of the previous lastconv output
+#pragma unroll
+    for (int c = 0; c < 9; ++c) acc_pos<K>(a0[1 + c], a1[1 + c], mf[c]);
+    acc_pos<K>(a0[10], a1[10], fl.x);
+    acc_pos<K>(a0[11], a1[11], fl.y);
+    acc_pos<K>(a0[12], a1[12], fl.z);
+    acc_pos<K>(a0[13], a1[13], fl.w);
+}
+
+template <typename FT, bool NHWC_HALF, int TMP_LAYOUT>
 __global__ void __launch_bounds__(kIfThreads)
 ifnet_assemble_kernel(const AssembleParams p)
 {
-    const int idx = blockIdx.x * kIfThreads + threadIdx.x;
+    const int gid = blockIdx.x * kIfThreads + threadIdx.x;
+    const int idx = gid >> 2, role = gid & 3;
     if (idx >= p.h * p.w) return;
+    const bool first = p.flow == nullptr;
+    if (first && role == 3) return;
     const int Y = idx / p.w, X = idx - Y * p.w;
     const int np = p.s == 1 ? 1 : 4;
     const int off = p.s == 1 ? 0 : p.s / 2 - 1;
     const size_t HW = (size_t)p.H * p.W;
-    const FT* f0 = reinterpret_cast<const FT*>(p.f0);
-    const FT* f1 = reinterpret_cast<const FT*>(p.f1);
+    const int bx = p.s * X + off, by = p.s * Y + off;
+    const float4* flow4 = reinterpret_cast<const float4*>(p.flow);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    int px[4], py[4];
-    WarpTap t0[4], t1[4];
-    float st[4][16];
+    float a0[16], a1[16];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (k >= np) break;
-        py[k] = p.s * Y + off + (k >> 1);
-        px[k] = p.s * X + off + (k & 1);
-        if (p.state) {
-            load16(p.state + ((size_t)py[k] * p.W + px[k]) * 16, st[k]);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) st[k][c] = 0.0f;
-        }
-        t0[k] = warp_tap(px[k], py[k], st[k][0], st[k][1], p.H, p.W);
-        t1[k] = warp_tap(px[k], py[k], st[k][2], st[k][3], p.H, p.W);
+    for (int c = 0; c < 16; ++c) { a0[c] = 0.0f; a1[c] = 0.0f; }
+    int n = 16;
+#define DRBA_FOR_POS(CALL)                                                                         \
+    {   { const int x = bx, y = by; const float4 fl = first ? zero4 : flow4[(size_t)y * p.W + x]; constexpr int K = 0; CALL; } \
+        if (np == 4) {                                                                             \
+            { const int x = bx + 1, y = by; const float4 fl = first ? zero4 : flow4[(size_t)y * p.W + x]; constexpr int K = 1; CALL; } \
+            { const int x = bx, y = by + 1; const float4 fl = first ? zero4 : flow4[(size_t)y * p.W + x]; constexpr int K = 2; CALL; } \
+            { const int x = bx + 1, y = by + 1; const float4 fl = first ? zero4 : flow4[(size_t)y * p.W + x]; constexpr int K = 3; CALL; } \
+        } }
+    if (role < 2) {
+        const FT* f = reinterpret_cast<const FT*>(role == 0 ? p.f0 : p.f1);
+        DRBA_FOR_POS((feat_pos<FT, K>(p, f, role, x, y, fl, a0, a1)))
+    } else if (role == 2) {
+        DRBA_FOR_POS((img_pos<K>(p, x, y, fl, HW, a0, a1)))
+        n = first ? 7 : 6;     // the first block carries the timestep here (no mask/feat/flow role)
+    } else {
+        DRBA_FOR_POS((misc_pos<TMP_LAYOUT, K>(p, x, y, fl, a0, a1)))
+        n = 14;
     }
-    float q[4], v[16];
-    // warped images (first block: the images themselves -- the identity warp is exact)
+#undef DRBA_FOR_POS
+    float v[16];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        for (int k = 0; k < np; ++k) q[k] = sample_plane(p.img0 + (size_t)c * HW, t0[k]);
-        v[c] = mean4(q, np);
-        for (int k = 0; k < np; ++k) q[k] = sample_plane(p.img1 + (size_t)c * HW, t1[k]);
-        v[3 + c] = mean4(q, np);
-    }
-    store_channels<NHWC_HALF>(p, Y, X, 0, v, 6);
-    // warped features
-    for (int side = 0; side < 2; ++side) {
-        float fq[4][16];
-        for (int k = 0; k < np; ++k) sample_feat16<FT>(side == 0 ? f0 : f1, side == 0 ? t0[k] : t1[k], fq[k]);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            for (int k = 0; k < np; ++k) q[k] = fq[k][c];
-            v[c] = mean4(q, np);
-        }
-        store_channels<NHWC_HALF>(p, Y, X, 6 + 16 * side, v, 16);
-    }
-    // timestep | mask | feat | flow / s
-    for (int k = 0; k < np; ++k) q[k] = p.timestep ? p.timestep[(size_t)py[k] * p.W + px[k]] : p.timestep_scalar;
-    v[0] = mean4(q, np);
-    int nch = 1;
-    if (p.state) {
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {   // mask (state ch 4), feat (5..12)
-            for (int k = 0; k < np; ++k) q[k] = st[k][4 + c];
-            v[1 + c] = mean4(q, np);
-        }
+    for (int c = 0; c < 16; ++c) v[c] = mean_pos(a0[c], a1[c], np);
+    if (role == 3) {
         const float inv = 1.0f / (float)p.s;   // IFNet_HDv3.py:87: interpolate(flow) * 1. / scale
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            for (int k = 0; k < np; ++k) q[k] = st[k][c];
-            v[10 + c] = mean4(q, np) * 1.0f * inv;
-        }
-        nch = 14;
+        for (int c = 10; c < 14; ++c) v[c] = v[c] * 1.0f * inv;
     }
-    store_channels<NHWC_HALF>(p, Y, X, 38, v, nch);
-    if (NHWC_HALF) {
-        const int used = 38 + nch;
-        __half* o = reinterpret_cast<__half*>(p.out) + ((size_t)Y * p.w + X) * p.out_cstride;
-        for (int c = used; c < p.out_cstride; ++c) o[c] = __float2half_rn(0.0f);
-    }
+    store16<NHWC_HALF>(p, Y, X, role, v, n);
 }
 
-// ---- lastconv output -> full-resolution state ----------------------------------------
-// TMP_LAYOUT 0: ConvTranspose output, NCHW fp32 [52][H/(2s)][W/(2s)] (PixelShuffle(2) is
-//               index arithmetic here: IFNet_HDv3.py:81)
-// TMP_LAYOUT 1: pixel-shuffled NHWC fp32 [H/s][W/s][16] (13 used), written by the tensor-core
-//               engine's lastconv epilogue
+// IFNet_HDv3.py:156-167: last flow update, warp both images, blend with sigmoid(mask)
 template <int TMP_LAYOUT>
-__device__ __forceinline__ void load_tmp13(const float* __restrict__ tmp, int yy, int xx, int h13, int w13, float* v)
-{
-    if (TMP_LAYOUT == 0) {
-        const int h2 = h13 >> 1, w2 = w13 >> 1;
-        const size_t base = (size_t)(yy >> 1) * w2 + (xx >> 1);
-        const int sub = (yy & 1) * 2 + (xx & 1);
-#pragma unroll
-        for (int c = 0; c < 13; ++c) v[c] = tmp[(size_t)(c * 4 + sub) * h2 * w2 + base];
-    } else {
-        float t[16];
-        load16(tmp + ((size_t)yy * w13 + xx) * 16, t);
-#pragma unroll
-        for (int c = 0; c < 13; ++c) v[c] = t[c];
-    }
-}
-
-template <int TMP_LAYOUT>
-__global__ void __launch_bounds__(kIfThreads)
-ifnet_upsample_kernel(const float* __restrict__ tmp, float* __restrict__ state, int accumulate, int H, int W, int s)
-{
-    const int idx = blockIdx.x * kIfThreads + threadIdx.x;
-    if (idx >= H * W) return;
-    const int y = idx / W, x = idx - y * W;
-    const int h13 = H / s, w13 = W / s;
-    const float r = 1.0f / (float)s;                   // ATen: ratio = 1 / scale_factor
-    float sy = r * ((float)y + 0.5f) - 0.5f, sx = r * ((float)x + 0.5f) - 0.5f;
-    if (sy < 0.0f) sy = 0.0f;
-    if (sx < 0.0f) sx = 0.0f;
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = y0 + (y0 < h13 - 1 ? 1 : 0), x1 = x0 + (x0 < w13 - 1 ? 1 : 0);
-    const float ly = sy - (float)y0, hy = 1.0f - ly, lx = sx - (float)x0, hx = 1.0f - lx;
-    float a[13], b[13], c[13], d[13];
-    load_tmp13<TMP_LAYOUT>(tmp, y0, x0, h13, w13, a);
-    load_tmp13<TMP_LAYOUT>(tmp, y0, x1, h13, w13, b);
-    load_tmp13<TMP_LAYOUT>(tmp, y1, x0, h13, w13, c);
-    load_tmp13<TMP_LAYOUT>(tmp, y1, x1, h13, w13, d);
-    float o[16];
-#pragma unroll
-    for (int k = 0; k < 13; ++k) o[k] = hy * (hx * a[k] + lx * b[k]) + ly * (hx * c[k] + lx * d[k]);
-    o[13] = o[14] = o[15] = 0.0f;
-    float4* dst = reinterpret_cast<float4*>(state + (size_t)idx * 16);
-    const float fs = (float)s;
-    float4 f = make_float4(o[0] * fs, o[1] * fs, o[2] * fs, o[3] * fs);   // IFNet_HDv3.py:93
-    if (accumulate) {                                                     // IFNet_HDv3.py:157
-        const float4 old = dst[0];
-        f.x = old.x + f.x; f.y = old.y + f.y; f.z = old.z + f.z; f.w = old.w + f.w;
-    }
-    dst[0] = f;
-    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-    dst[2] = make_float4(o[8], o[9], o[10], o[11]);
-    dst[3] = make_float4(o[12], 0.0f, 0.0f, 0.0f);
-}
-
-// IFNet_HDv3.py:160-167: warp both images with the final flow, blend with sigmoid(mask)
 __global__ void __launch_bounds__(kIfThreads)
 ifnet_blend_kernel(const float* __restrict__ img0, const float* __restrict__ img1,
-                   const float* __restrict__ state, float* __restrict__ out, int H, int W)
+                   const float* __restrict__ flow, const Tmp13 t, float* __restrict__ out, int H, int W)
 {
     const int idx = blockIdx.x * kIfThreads + threadIdx.x;
     if (idx >= H * W) return;
     const int y = idx / W, x = idx - y * W;
-    const float4* st = reinterpret_cast<const float4*>(state + (size_t)idx * 16);
-    const float4 fl = st[0];
-    const float mk = st[1].x;
+    float o[5];
+    up_tmp<TMP_LAYOUT, 0, 5>(t, y, x, o);
+    const float fs = (float)t.s;
+    float4 fl = make_float4(o[0] * fs, o[1] * fs, o[2] * fs, o[3] * fs);
+    if (flow) {
+        const float4 old = reinterpret_cast<const float4*>(flow)[idx];
+        fl.x = old.x + fl.x; fl.y = old.y + fl.y; fl.z = old.z + fl.z; fl.w = old.w + fl.w;
+    }
     const WarpTap t0 = warp_tap(x, y, fl.x, fl.y, H, W);
     const WarpTap t1 = warp_tap(x, y, fl.z, fl.w, H, W);
-    const float m = 1.0f / (1.0f + expf(-mk));
+    const float m = 1.0f / (1.0f + expf(-o[4]));
     const size_t HW = (size_t)H * W;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -291,74 +373,83 @@ ifnet_blend_kernel(const float* __restrict__ img0, const float* __restrict__ img
     }
 }
 
-// state[..., 0:4] -> NCHW flow [4][H][W] (calc_flow needs block0's flow as planar tensors)
-__global__ void __launch_bounds__(kIfThreads)
-ifnet_state_flow_kernel(const float* __restrict__ state, float* __restrict__ flow, int HW)
-{
-    const int idx = blockIdx.x * kIfThreads + threadIdx.x;
-    if (idx >= HW) return;
-    const float4 f = reinterpret_cast<const float4*>(state + (size_t)idx * 16)[0];
-    flow[idx] = f.x; flow[(size_t)HW + idx] = f.y; flow[(size_t)2 * HW + idx] = f.z; flow[(size_t)3 * HW + idx] = f.w;
-}
-
 }  // namespace drba
 
 using namespace drba;
 
+static int tmp_ok(const float* tmp, int layout, int H, int W, int s)
+{
+    if (!tmp || (layout != 0 && layout != 1) || s <= 0 || H % s != 0 || W % s != 0) return DRBA_E_ARG;
+    if (layout == 0 && ((H / s) % 2 != 0 || (W / s) % 2 != 0)) return DRBA_E_ARG;
+    if (layout == 1 && !aligned16(tmp)) return DRBA_E_ALIGN;
+    return DRBA_OK;
+}
+
 extern "C" {
 
 int drba_ifnet_assemble(const float* img0, const float* img1, const void* f0, const void* f1, int feat_dtype,
-                        const float* timestep, float timestep_scalar, const float* state,
+                        const float* timestep, float timestep_scalar,
+                        const float* flow, const float* tmp_prev, int tmp_layout, int s_prev,
                         void* out, int out_dtype, int out_cstride, int H, int W, int s, void* stream)
 {
     if (H <= 0 || W <= 0 || s <= 0 || (s & (s - 1)) != 0 || H % s != 0 || W % s != 0) return DRBA_E_ARG;
     if (!img0 || !img1 || !f0 || !f1 || !out) return DRBA_E_ARG;
     if (feat_dtype != DRBA_F32 && feat_dtype != DRBA_F16) return DRBA_E_ARG;
     if (out_dtype != DRBA_F32 && out_dtype != DRBA_F16) return DRBA_E_ARG;
-    const int nch = state ? 52 : 39;
-    if (out_dtype == DRBA_F16 && out_cstride < nch) return DRBA_E_ARG;
-    if (!aligned16(f0) || !aligned16(f1) || (state && !aligned16(state))) return DRBA_E_ALIGN;
+    if (out_dtype == DRBA_F16 && (out_cstride < (flow ? 64 : 48) || out_cstride % 8 != 0)) return DRBA_E_ARG;
+    if (!aligned16(f0) || !aligned16(f1) || !aligned16(out) || (flow && !aligned16(flow))) return DRBA_E_ALIGN;
+    if (flow) {
+        const int rc = tmp_ok(tmp_prev, tmp_layout, H, W, s_prev);
+        if (rc != DRBA_OK) return rc;
+    }
     AssembleParams p;
     p.img0 = img0; p.img1 = img1; p.f0 = f0; p.f1 = f1;
-    p.timestep = timestep; p.timestep_scalar = timestep_scalar; p.state = state;
+    p.timestep = timestep; p.timestep_scalar = timestep_scalar; p.flow = flow;
+    p.prev.p = tmp_prev; p.prev.s = flow ? s_prev : 1; p.prev.h13 = flow ? H / s_prev : 1; p.prev.w13 = flow ? W / s_prev : 1;
     p.out = out; p.out_cstride = out_cstride; p.H = H; p.W = W; p.s = s; p.h = H / s; p.w = W / s;
-    const unsigned grid = cdiv((size_t)p.h * p.w, kIfThreads);
+    const unsigned grid = cdiv((size_t)p.h * p.w * 4, kIfThreads);
     cudaStream_t st = as_stream(stream);
-    if (feat_dtype == DRBA_F32 && out_dtype == DRBA_F32) ifnet_assemble_kernel<float, false><<<grid, kIfThreads, 0, st>>>(p);
-    else if (feat_dtype == DRBA_F16 && out_dtype == DRBA_F16) ifnet_assemble_kernel<__half, true><<<grid, kIfThreads, 0, st>>>(p);
-    else if (feat_dtype == DRBA_F32 && out_dtype == DRBA_F16) ifnet_assemble_kernel<float, true><<<grid, kIfThreads, 0, st>>>(p);
-    else ifnet_assemble_kernel<__half, false><<<grid, kIfThreads, 0, st>>>(p);
+    const int key = (feat_dtype == DRBA_F16 ? 4 : 0) | (out_dtype == DRBA_F16 ? 2 : 0) | (tmp_layout == 1 ? 1 : 0);
+    switch (key) {
+        case 0: ifnet_assemble_kernel<float, false, 0><<<grid, kIfThreads, 0, st>>>(p); break;
+        case 1: ifnet_assemble_kernel<float, false, 1><<<grid, kIfThreads, 0, st>>>(p); break;
+        case 2: ifnet_assemble_kernel<float, true, 0><<<grid, kIfThreads, 0, st>>>(p); break;
+        case 3: ifnet_assemble_kernel<float, true, 1><<<grid, kIfThreads, 0, st>>>(p); break;
+        case 4: ifnet_assemble_kernel<__half, false, 0><<<grid, kIfThreads, 0, st>>>(p); break;
+        case 5: ifnet_assemble_kernel<__half, false, 1><<<grid, kIfThreads, 0, st>>>(p); break;
+        case 6: ifnet_assemble_kernel<__half, true, 0><<<grid, kIfThreads, 0, st>>>(p); break;
+        default: ifnet_assemble_kernel<__half, true, 1><<<grid, kIfThreads, 0, st>>>(p); break;
+    }
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
 }
 
-int drba_ifnet_upsample(const float* tmp, int tmp_layout, float* state, int accumulate, int H, int W, int s, void* stream)
+int drba_ifnet_flow_accum(const float* tmp, int tmp_layout, int s, float* flow, float* planar, int accumulate,
+                          int H, int W, void* stream)
 {
-    if (H <= 0 || W <= 0 || s <= 0 || H % s != 0 || W % s != 0 || !tmp || !state) return DRBA_E_ARG;
-    if (tmp_layout != 0 && tmp_layout != 1) return DRBA_E_ARG;
-    if (tmp_layout == 0 && ((H / s) % 2 != 0 || (W / s) % 2 != 0)) return DRBA_E_ARG;
-    if (!aligned16(state) || (tmp_layout == 1 && !aligned16(tmp))) return DRBA_E_ALIGN;
+    if (H <= 0 || W <= 0 || (!flow && !planar) || (accumulate && !flow)) return DRBA_E_ARG;
+    const int rc = tmp_ok(tmp, tmp_layout, H, W, s);
+    if (rc != DRBA_OK) return rc;
+    if (flow && !aligned16(flow)) return DRBA_E_ALIGN;
+    Tmp13 t; t.p = tmp; t.s = s; t.h13 = H / s; t.w13 = W / s;
+    const unsigned grid = cdiv((size_t)H * W, 256);
+    if (tmp_layout == 0) ifnet_flow_accum_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(t, flow, planar, accumulate, H, W);
+    else ifnet_flow_accum_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(t, flow, planar, accumulate, H, W);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+int drba_ifnet_blend(const float* img0, const float* img1, const float* flow, const float* tmp, int tmp_layout, int s,
+                     float* out, int H, int W, void* stream)
+{
+    if (H <= 0 || W <= 0 || !img0 || !img1 || !out) return DRBA_E_ARG;
+    const int rc = tmp_ok(tmp, tmp_layout, H, W, s);
+    if (rc != DRBA_OK) return rc;
+    if (flow && !aligned16(flow)) return DRBA_E_ALIGN;
+    Tmp13 t; t.p = tmp; t.s = s; t.h13 = H / s; t.w13 = W / s;
     const unsigned grid = cdiv((size_t)H * W, kIfThreads);
-    if (tmp_layout == 0) ifnet_upsample_kernel<0><<<grid, kIfThreads, 0, as_stream(stream)>>>(tmp, state, accumulate, H, W, s);
-    else ifnet_upsample_kernel<1><<<grid, kIfThreads, 0, as_stream(stream)>>>(tmp, state, accumulate, H, W, s);
-    DRBA_RETURN_IF_LAUNCH_FAILED();
-    return DRBA_OK;
-}
-
-int drba_ifnet_blend(const float* img0, const float* img1, const float* state, float* out, int H, int W, void* stream)
-{
-    if (H <= 0 || W <= 0 || !img0 || !img1 || !state || !out) return DRBA_E_ARG;
-    if (!aligned16(state)) return DRBA_E_ALIGN;
-    ifnet_blend_kernel<<<cdiv((size_t)H * W, kIfThreads), kIfThreads, 0, as_stream(stream)>>>(img0, img1, state, out, H, W);
-    DRBA_RETURN_IF_LAUNCH_FAILED();
-    return DRBA_OK;
-}
-
-int drba_ifnet_state_flow(const float* state, float* flow, int H, int W, void* stream)
-{
-    if (H <= 0 || W <= 0 || !state || !flow) return DRBA_E_ARG;
-    if (!aligned16(state)) return DRBA_E_ALIGN;
-    ifnet_state_flow_kernel<<<cdiv((size_t)H * W, kIfThreads), kIfThreads, 0, as_stream(stream)>>>(state, flow, H * W);
+    if (tmp_layout == 0) ifnet_blend_kernel<0><<<grid, kIfThreads, 0, as_stream(stream)>>>(img0, img1, flow, t, out, H, W);
+    else ifnet_blend_kernel<1><<<grid, kIfThreads, 0, as_stream(stream)>>>(img0, img1, flow, t, out, H, W);
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
 }

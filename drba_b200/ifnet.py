@@ -87,15 +87,34 @@ def _pad16(n):
     return (n + 15) // 16 * 16
 
 
-def _tc_conv3x3(weight, bias, stride, act, device, beta=None):
+def _packed_input_channels(first):
+    """Packed channel -> reference channel of an IFBlock's conv input as written by
+    drba_ifnet_assemble (NHWC fp16): [f0 16 | f1 16 | img0 3, img1 3, (first: timestep), 0.. |
+    timestep, mask, feat 8, flow 4, 0, 0]; -1 = zero padding.  See csrc/ifnet.cu ref_channel()."""
+    m = [6 + k for k in range(16)] + [22 + k for k in range(16)]
+    m += [0, 1, 2, 3, 4, 5] + ([38] if first else [-1]) + [-1] * 9
+    if not first:
+        m += [38 + k for k in range(14)] + [-1, -1]
+    return m
+
+
+def _tc_conv3x3(weight, bias, stride, act, device, beta=None, in_map=None):
     w, b = _pack_conv3x3(weight, bias, beta)           # [9][Cin][Cout]
     T, cin, cout = w.shape
+    if in_map is not None:                             # permute / pad the input channels
+        wm = torch.zeros((T, len(in_map), cout))
+        for pc, rc in enumerate(in_map):
+            if rc >= 0:
+                wm[:, pc, :] = w[:, rc, :]
+        w, cin_real, cin = wm, cin, len(in_map)
+    else:
+        cin_real = cin
     wp = torch.zeros((1, T, _pad16(cout), _pad16(cin)))
     wp[0, :, :cout, :cin] = w.permute(0, 2, 1)
     bp = torch.zeros((1, _pad16(cout)))
     bp[0, :cout] = b
     dy, dx = _taps3x3()
-    return _TcLayer(wp, bp, dy, dx, stride, act, cout, 0, device, cin_real=cin)
+    return _TcLayer(wp, bp, dy, dx, stride, act, cout, 0, device, cin_real=cin_real)
 
 
 def _tc_lastconv(weight, bias, device):
@@ -150,7 +169,8 @@ class IFNetEngine:
         self.tc = {}
         if precision == "fp16":
             for name, cin, c in _BLOCKS:
-                self.tc[f"{name}.conv0a"] = _tc_conv3x3(sd[f"{name}.conv0.0.0.weight"], sd[f"{name}.conv0.0.0.bias"], 2, 1, d)
+                self.tc[f"{name}.conv0a"] = _tc_conv3x3(sd[f"{name}.conv0.0.0.weight"], sd[f"{name}.conv0.0.0.bias"], 2, 1, d,
+                                                        in_map=_packed_input_channels(name == "block0"))
                 self.tc[f"{name}.conv0b"] = _tc_conv3x3(sd[f"{name}.conv0.1.0.weight"], sd[f"{name}.conv0.1.0.bias"], 2, 1, d)
                 for i in range(8):
                     p = f"{name}.convblock.{i}"
@@ -175,8 +195,9 @@ class IFNetEngine:
         return _lib.launch(name, 1, flops, nbytes)
 
     def _conv_direct(self, layer, x_ptr, H, W, in_strides, out_t, OH, OW, out_strides, OS=1, PY=0, PX=0, res_ptr=None):
+        out_dtype = 1 if out_t.dtype == torch.float16 else 0
         with self._launch("conv_direct_f32", flops=2.0 * layer.T * layer.cin * layer.cout * OH * OW):
-            rc = self.L.drba_conv2d_direct_f32(x_ptr, ptr(layer.w), ptr(layer.b), res_ptr, ptr(out_t),
+            rc = self.L.drba_conv2d_direct_f32(x_ptr, ptr(layer.w), ptr(layer.b), res_ptr, ptr(out_t), out_dtype,
                                                1, layer.cin, H, W, _LL4(*in_strides),
                                                layer.cout, OH, OW, _LL4(*out_strides),
                                                layer.stride, OS, PY, PX, layer.T, layer.dy, layer.dx,
@@ -197,7 +218,8 @@ class IFNetEngine:
 
     # ------------------------------------------------------------------ Head (IFNet_HDv3.py:28-47)
     def encode(self, img):
-        """img [1,3,H,W] fp32 -> feature map [H][W][16] (NHWC; fp32 in the exact engine)."""
+        """img [1,3,H,W] fp32 -> feature map [H][W][16] (NHWC; fp32 in the exact engine, fp16 in the
+        tensor-core engine)."""
         require_cuda(img)
         img = img.float().contiguous()
         _, _, H, W = img.shape
@@ -205,7 +227,8 @@ class IFNetEngine:
         h2, w2 = H // 2, W // 2
         a = self._buf(("enc_a", H, W), (16, h2, w2))
         b = self._buf(("enc_b", H, W), (16, h2, w2))
-        feat = torch.empty((H, W, 16), dtype=torch.float32, device=self.device)
+        feat = torch.empty((H, W, 16), dtype=torch.float16 if self.precision == "fp16" else torch.float32,
+                           device=self.device)
         with torch.cuda.device(self.device):
             self._conv_direct(self.direct["encode.cnn0"], ptr(img), H, W, self._nchw(3, H, W), a, h2, w2, self._nchw(16, h2, w2))
             self._conv_direct(self.direct["encode.cnn1"], ptr(a), h2, w2, self._nchw(16, h2, w2), b, h2, w2, self._nchw(16, h2, w2))
@@ -218,20 +241,42 @@ class IFNetEngine:
         return feat
 
     # ------------------------------------------------------------------ IFBlock (IFNet_HDv3.py:84-96)
-    def _block(self, bi, img0, img1, f0, f1, timestep, ts_scalar, state, H, W, s):
+    def _assemble(self, out, out_dtype, cstride, img0, img1, f0, f1, timestep, ts_scalar, flow, prev, H, W, s):
+        tmp_prev, layout_prev, s_prev = prev if prev is not None else (None, 0, 1)
+        with self._launch("ifnet_assemble"):
+            rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 1 if f0.dtype == torch.float16 else 0,
+                                            ptr(timestep), float(ts_scalar),
+                                            None if prev is None else ptr(flow), ptr(tmp_prev), layout_prev, s_prev,
+                                            ptr(out), out_dtype, cstride, H, W, s, stream_ptr(self.device))
+        self._check(rc, "drba_ifnet_assemble")
+
+    def _block(self, bi, img0, img1, f0, f1, timestep, ts_scalar, flow, prev, H, W, s):
+        """Runs block `bi`; returns (tmp, layout, s): its lastconv output (13 ch at 1/s)."""
         name, cin, c = _BLOCKS[bi]
         h, w = H // s, W // s
         assert H % (4 * s) == 0 and W % (4 * s) == 0, "frame size must be a multiple of 4 * scale"
-        first = bi == 0
-        if self.precision == "fp16":
-            return self._block_tc(bi, img0, img1, f0, f1, timestep, ts_scalar, state, H, W, s)
-        x = self._buf(("x", bi, H, W), (cin, h, w))
-        with self._launch("ifnet_assemble"):
-            rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 0,
-                                            ptr(timestep), float(ts_scalar), None if first else ptr(state),
-                                            ptr(x), 0, 0, H, W, s, stream_ptr(self.device))
-        self._check(rc, "drba_ifnet_assemble")
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+        if self.precision == "fp16":
+            # tensor-core engine: NHWC fp16 activations, 11 conv launches
+            f16 = torch.float16
+            cin_pad = 48 if bi == 0 else 64
+            x = self._buf(("xh", bi, H, W), (h, w, cin_pad), f16)
+            self._assemble(x, 1, cin_pad, img0, img1, f0, f1, timestep, ts_scalar, flow, prev, H, W, s)
+            a = self._buf(("ah", bi, H, W), (h2, w2, c // 2), f16)
+            self._conv_tc(self.tc[f"{name}.conv0a"], x, h, w, a, h2, w2, c // 2)
+            p0 = self._buf(("p0h", bi, H, W), (h4, w4, c), f16)
+            p1 = self._buf(("p1h", bi, H, W), (h4, w4, c), f16)
+            self._conv_tc(self.tc[f"{name}.conv0b"], a, h2, w2, p0, h4, w4, c)
+            cur, nxt = p0, p1
+            for i in range(8):
+                self._conv_tc(self.tc[f"{name}.res{i}"], cur, h4, w4, nxt, h4, w4, c, res=cur)
+                cur, nxt = nxt, cur
+            tmp = self._buf(("tmp13", bi, H, W), (h, w, 16), torch.float32)
+            self._conv_tc(self.tc[f"{name}.last"], cur, h4, w4, tmp, h4, w4, 16)
+            return tmp, 1, s
+        # exact engine: NCHW fp32 activations
+        x = self._buf(("x", bi, H, W), (cin, h, w))
+        self._assemble(x, 0, 0, img0, img1, f0, f1, timestep, ts_scalar, flow, prev, H, W, s)
         a = self._buf(("a", bi, H, W), (c // 2, h2, w2))
         self._conv_direct(self.direct[f"{name}.conv0a"], ptr(x), h, w, self._nchw(cin, h, w), a, h2, w2, self._nchw(c // 2, h2, w2))
         p0 = self._buf(("p0", bi, H, W), (c, h4, w4))
@@ -247,38 +292,14 @@ class IFNetEngine:
             for px in (0, 1):
                 self._conv_direct(self.direct[f"{name}.last{py}{px}"], ptr(cur), h4, w4, st4, ct, h4, w4,
                                   self._nchw(52, h2, w2), OS=2, PY=py, PX=px)
-        with self._launch("ifnet_upsample"):
-            rc = self.L.drba_ifnet_upsample(ptr(ct), 0, ptr(state), 0 if first else 1, H, W, s, stream_ptr(self.device))
-        self._check(rc, "drba_ifnet_upsample")
+        return ct, 0, s
 
-    def _block_tc(self, bi, img0, img1, f0, f1, timestep, ts_scalar, state, H, W, s):
-        """Same schedule on the tensor-core engine: NHWC fp16 activations, 11 conv launches."""
-        name, cin, c = _BLOCKS[bi]
-        h, w = H // s, W // s
-        first = bi == 0
-        h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
-        cin_pad = _pad16(cin)
-        f16 = torch.float16
-        x = self._buf(("xh", bi, H, W), (h, w, cin_pad), f16)
-        with self._launch("ifnet_assemble"):
-            rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 0 if f0.dtype == torch.float32 else 1,
-                                            ptr(timestep), float(ts_scalar), None if first else ptr(state),
-                                            ptr(x), 1, cin_pad, H, W, s, stream_ptr(self.device))
-        self._check(rc, "drba_ifnet_assemble")
-        a = self._buf(("ah", bi, H, W), (h2, w2, c // 2), f16)
-        self._conv_tc(self.tc[f"{name}.conv0a"], x, h, w, a, h2, w2, c // 2)
-        p0 = self._buf(("p0h", bi, H, W), (h4, w4, c), f16)
-        p1 = self._buf(("p1h", bi, H, W), (h4, w4, c), f16)
-        self._conv_tc(self.tc[f"{name}.conv0b"], a, h2, w2, p0, h4, w4, c)
-        cur, nxt = p0, p1
-        for i in range(8):
-            self._conv_tc(self.tc[f"{name}.res{i}"], cur, h4, w4, nxt, h4, w4, c, res=cur)
-            cur, nxt = nxt, cur
-        tmp = self._buf(("tmp13", bi, H, W), (h, w, 16), torch.float32)
-        self._conv_tc(self.tc[f"{name}.last"], cur, h4, w4, tmp, h4, w4, 16)
-        with self._launch("ifnet_upsample"):
-            rc = self.L.drba_ifnet_upsample(ptr(tmp), 1, ptr(state), 0 if first else 1, H, W, s, stream_ptr(self.device))
-        self._check(rc, "drba_ifnet_upsample")
+    def _flow_accum(self, prev, flow, planar, accumulate, H, W):
+        tmp, layout, s = prev
+        with self._launch("ifnet_flow_accum", nbytes=float(H * W * (32 if accumulate else 16) + (16 * H * W if planar is not None else 0))):
+            rc = self.L.drba_ifnet_flow_accum(ptr(tmp), layout, s, ptr(flow), ptr(planar), 1 if accumulate else 0,
+                                              H, W, stream_ptr(self.device))
+        self._check(rc, "drba_ifnet_flow_accum")
 
     @staticmethod
     def _int_scale(s):
@@ -299,12 +320,17 @@ class IFNetEngine:
         with torch.cuda.device(self.device):
             f0 = self.encode(img0) if f0 is None else f0
             f1 = self.encode(img1) if f1 is None else f1
-            state = self._buf(("state", H, W), (H, W, 16))
+            flow = self._buf(("flow", H, W), (H, W, 4))
+            prev = None
             for bi in range(5):
-                self._block(bi, img0, img1, f0, f1, ts_t, ts_s, state, H, W, self._int_scale(scale_list[bi]))
+                if bi > 0:     # flow (+)= s * up(previous lastconv[0:4])
+                    self._flow_accum(prev, flow, None, bi > 1, H, W)
+                prev = self._block(bi, img0, img1, f0, f1, ts_t, ts_s, flow, prev, H, W, self._int_scale(scale_list[bi]))
             out = torch.empty((1, 3, H, W), dtype=torch.float32, device=self.device)
-            with self._launch("ifnet_blend"):
-                rc = self.L.drba_ifnet_blend(ptr(img0), ptr(img1), ptr(state), ptr(out), H, W, stream_ptr(self.device))
+            tmp, layout, s = prev
+            with self._launch("ifnet_blend", nbytes=float(H * W * (16 + 24 + 12))):
+                rc = self.L.drba_ifnet_blend(ptr(img0), ptr(img1), ptr(flow), ptr(tmp), layout, s, ptr(out), H, W,
+                                             stream_ptr(self.device))
             self._check(rc, "drba_ifnet_blend")
         return out
 
@@ -314,10 +340,7 @@ class IFNetEngine:
         img0, img1 = img0.float().contiguous(), img1.float().contiguous()
         _, _, H, W = img0.shape
         with torch.cuda.device(self.device):
-            state = self._buf(("state0", H, W), (H, W, 16))
-            self._block(0, img0, img1, f0, f1, None, float(timestep), state, H, W, self._int_scale(scale))
+            prev = self._block(0, img0, img1, f0, f1, None, float(timestep), None, None, H, W, self._int_scale(scale))
             flow = torch.empty((1, 4, H, W), dtype=torch.float32, device=self.device)
-            with self._launch("ifnet_state_flow"):
-                rc = self.L.drba_ifnet_state_flow(ptr(state), ptr(flow), H, W, stream_ptr(self.device))
-            self._check(rc, "drba_ifnet_state_flow")
+            self._flow_accum(prev, None, flow, False, H, W)
         return flow

@@ -131,7 +131,8 @@ DRBA_API int drba_resize_bilinear_f32(const float* in, float* out, int N, int C,
  * in_strides / out_strides: element strides {n, c, y, x}; `res` (optional) is addressed
  * like `out`.  w is packed [T][Cin][Cout] fp32.  act: 0 none, 1 LeakyReLU(0.2).
  * ------------------------------------------------------------------------- */
-DRBA_API int drba_conv2d_direct_f32(const float* in, const float* w, const float* bias, const float* res, float* out,
+DRBA_API int drba_conv2d_direct_f32(const float* in, const float* w, const float* bias, const void* res, void* out,
+                                    int out_dtype /* DRBA_F32 | DRBA_F16: dtype of out (and res) */,
                                     int N, int Cin, int H, int W, const long long* in_strides,
                                     int Cout, int OH, int OW, const long long* out_strides,
                                     int S, int OS, int PY, int PX, int T, const int* dy, const int* dx,
@@ -156,23 +157,32 @@ DRBA_API int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
 
 /* ---------------------------------------------------------------------------
  * Fused non-conv stages of IFNet.forward (IFNet_HDv3.py:126-177), batch 1.
- * feature maps f0/f1: [H][W][16] (NHWC) of feat_dtype; state: [H][W][16] fp32 =
- * {flow 4, mask 1, feat 8, pad 3}.
- * drba_ifnet_assemble: conv input of one IFBlock at 1/s resolution (warp + cat + resize,
- *   IFNet_HDv3.py:151-155 + :85-88).  state == NULL: first block (39 channels, no warp).
- *   out_dtype DRBA_F32: NCHW [52|39][H/s][W/s]; DRBA_F16: NHWC [H/s][W/s][out_cstride].
- * drba_ifnet_upsample: lastconv output -> x s bilinear -> state (IFNet_HDv3.py:91-96,:156-158).
- *   tmp_layout 0: ConvT output NCHW fp32 [52][H/2s][W/2s]; 1: NHWC fp32 [H/s][W/s][16].
- * drba_ifnet_blend: IFNet_HDv3.py:160-167.   drba_ifnet_state_flow: state -> [4][H][W].
+ * Feature maps f0/f1: [H][W][16] (NHWC) of feat_dtype.  The only full-resolution state is
+ * flow: [H][W][4] fp32.  "tmp" = a block's lastconv output, 13 channels at 1/s resolution:
+ *   tmp_layout 0: ConvTranspose output NCHW fp32 [52][H/2s][W/2s] (exact engine)
+ *   tmp_layout 1: pixel-shuffled NHWC fp32 [H/s][W/s][16]       (tensor-core engine)
+ *
+ * drba_ifnet_assemble: conv input of one IFBlock at 1/s resolution = warp + cat + resize
+ *   (IFNet_HDv3.py:151-155 + :85-88).  flow == NULL: first block (39 channels, no warp).
+ *   Otherwise mask/feat are taken from tmp_prev (x s_prev bilinear, IFNet_HDv3.py:92-96).
+ *   out_dtype DRBA_F32: NCHW [52|39][H/s][W/s] in the reference's channel order;
+ *   out_dtype DRBA_F16: NHWC [H/s][W/s][out_cstride] in the packed order
+ *     [f0 16 | f1 16 | img0 3, img1 3, (first block: timestep), 0.. | timestep, mask, feat 8, flow 4, 0, 0]
+ *     (48 channels for the first block, 64 otherwise; conv weights are permuted to match).
+ * drba_ifnet_flow_accum: flow (+)= s * up(tmp[0:4]) (IFNet_HDv3.py:91-93, :157); `planar`
+ *   (optional) also receives the result as [4][H][W] (RIFE.calc_flow needs planar flows).
+ * drba_ifnet_blend: last flow update + warps + sigmoid blend (IFNet_HDv3.py:156-167):
+ *   out[3][H][W] = warp(img0, F[:2]) * m + warp(img1, F[2:4]) * (1 - m),
+ *   F = flow + s * up(tmp[0:4]) (flow may be NULL), m = sigmoid(up(tmp[4])).
  * ------------------------------------------------------------------------- */
 DRBA_API int drba_ifnet_assemble(const float* img0, const float* img1, const void* f0, const void* f1, int feat_dtype,
-                                 const float* timestep, float timestep_scalar, const float* state,
+                                 const float* timestep, float timestep_scalar,
+                                 const float* flow, const float* tmp_prev, int tmp_layout, int s_prev,
                                  void* out, int out_dtype, int out_cstride, int H, int W, int s, void* stream);
-DRBA_API int drba_ifnet_upsample(const float* tmp, int tmp_layout, float* state, int accumulate,
-                                 int H, int W, int s, void* stream);
-DRBA_API int drba_ifnet_blend(const float* img0, const float* img1, const float* state, float* out,
-                              int H, int W, void* stream);
-DRBA_API int drba_ifnet_state_flow(const float* state, float* flow, int H, int W, void* stream);
+DRBA_API int drba_ifnet_flow_accum(const float* tmp, int tmp_layout, int s, float* flow, float* planar, int accumulate,
+                                   int H, int W, void* stream);
+DRBA_API int drba_ifnet_blend(const float* img0, const float* img1, const float* flow, const float* tmp, int tmp_layout,
+                              int s, float* out, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }
