@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-family breakdown here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -194,7 +195,7 @@ def main():
     from drba_b200 import _lib
     from drba_b200.rife import RIFE
     state, wdesc = load_state()
-    model = RIFE(state=state, device=dev, precision=args.precision)
+    model = RIFE(state=state, device=dev, precision=args.precision, graphs=not args.no_graphs)
     h, w = net_size(H_SRC, W_SRC, model.scale, model.pad_size)
     K, Wm = args.steps, args.warmup
     ring = 8
@@ -266,11 +267,18 @@ def main():
     clk = clocks.stop()
 
     # ---- instrumented pass: per-kernel-family shares and the roofline ------------------------------
+    model.graphs = False          # per-kernel events need eager launches
+    _, reuse = window(Wm + K - 1, None, frames)
     with _lib.LaunchProfiler() as prof:
         for j in range(Wm + K, Wm + K + min(K, 6)):
             _, reuse = window(j, reuse, frames)
-        fam = prof.summary()
+        detail = prof.summary()
     nprof = min(K, 6)
+    fam = {}
+    for k, v in detail.items():           # aggregate "family/tag" -> family
+        d = fam.setdefault(k.split("/")[0], {"calls": 0, "kernels": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        for key in d:
+            d[key] += v[key]
 
     # ---- max over ranks -------------------------------------------------------------------------
     t = torch.tensor([ms, ms_e], dtype=torch.float64, device=dev)
@@ -303,7 +311,11 @@ def main():
                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         if args.profile_json:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_json)), exist_ok=True)
-            json.dump(breakdown, open(args.profile_json, "w"), indent=1)
+            per_tag = {k: {"ms_per_step": round(v["ms"] / nprof, 4), "kernels_per_step": round(v["kernels"] / nprof, 1),
+                           "avg_us": round(1e3 * v["ms"] / max(v["kernels"], 1), 2),
+                           "TFLOPs": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["flops"] else None}
+                       for k, v in sorted(detail.items(), key=lambda kv: -kv[1]["ms"])}
+            json.dump({"families": breakdown, "detail": per_tag}, open(args.profile_json, "w"), indent=1)
         print("per-kernel-family breakdown (instrumented pass): " + json.dumps(breakdown), file=sys.stderr)
 
         cpu = None
@@ -321,6 +333,7 @@ def main():
                            "weights": wdesc, "precision": args.precision + " convs (tcgen05), fp32 flow/DRM/warp/splat"
                            if args.precision == "fp16" else "fp32",
                            "parallelism": f"frame-window shards x{world}, no collective",
+                           "launch": "eager" if args.no_graphs else "one CUDA graph replay per window shape",
                            "l2": "per-step working set (3 fp32 frames 75 MB + 134 MB state + features/activations) exceeds the 126 MB L2; ring of 8 distinct frames"},
                 "e2e": {"value": round(nout_e_all / (ms_e * 1e-3), 3), "unit": UNIT,
                         "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K)},

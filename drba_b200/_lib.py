@@ -36,7 +36,7 @@ SIGNATURES = {
     "drba_resize_bilinear_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "drba_conv2d_direct_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P,
                                     _I, _I, _I, _I, _I, _P, _P, _I, _P]),
-    "drba_conv_tc_f16": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "drba_conv_tc_f16": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     "drba_ifnet_assemble": (_I, [_P, _P, _P, _P, _I, _P, _F, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
     "drba_ifnet_flow_accum": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P]),
     "drba_ifnet_blend": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P]),

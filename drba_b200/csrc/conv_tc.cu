@@ -50,6 +50,7 @@ struct TcParams {
     const __half* res;      // NHWC fp16, same geometry as out (or NULL)
     void* out;
     int out_cstride;        // channels per pixel in `out` (epilogue 0)
+    int os;                 // epilogue 0: output placement stride; group g = phase (py, px) lands at (os*oy + py, os*ox + px)
     int tiles_x;
 };
 
@@ -209,7 +210,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         const float* bias = p.bias + (size_t)g * p.cout_pad + nsplit * p.ntile;
         if (p.epilogue == 0) {
-            const size_t pix = (size_t)oy * p.OW + ox;
+            const size_t pix = p.os == 1 ? (size_t)oy * p.OW + ox
+                                         : (size_t)(oy * p.os + (g >> 1)) * (p.OW * p.os) + (ox * p.os + (g & 1));
             __half* out = reinterpret_cast<__half*>(p.out) + pix * p.out_cstride + nsplit * p.ntile;
             const __half* res = p.res ? p.res + pix * p.out_cstride + nsplit * p.ntile : nullptr;
             for (int c0 = 0; c0 < p.ntile; c0 += 16) {
@@ -304,7 +306,7 @@ extern "C" {
 int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
                      const void* w, const float* bias, int G, int T, const int* dy, const int* dx,
                      int cout_pad, int cout, int S, int OH, int OW,
-                     int epilogue, int act, const void* res, void* out, int out_cstride, void* stream)
+                     int epilogue, int act, const void* res, void* out, int out_cstride, int out_os, void* stream)
 {
     if (!in || !w || !bias || !out || !dy || !dx) return DRBA_E_ARG;
     if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || Cin <= 0 || Cin % 16 != 0) return DRBA_E_ARG;
@@ -314,6 +316,8 @@ int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
     if (cout_pad <= 0 || cout_pad % 16 != 0 || cout <= 0 || cout > cout_pad) return DRBA_E_ARG;
     if (epilogue != 0 && epilogue != 1) return DRBA_E_ARG;
     if (epilogue == 1 && (cout_pad != 64 || cout != 52 || G != 4)) return DRBA_E_ARG;
+    if (out_os != 1 && out_os != 2) return DRBA_E_ARG;
+    if (epilogue == 0 && ((out_os == 1 && G != 1) || (out_os == 2 && G != 4))) return DRBA_E_ARG;
     if (epilogue == 0 && (out_cstride < cout_pad || out_cstride % 8 != 0)) return DRBA_E_ARG;
     if (!aligned16(in) || !aligned16(w) || !aligned16(out) || (res && !aligned16(res))) return DRBA_E_ALIGN;
     EncodeTiledFn encode = get_encode();
@@ -337,7 +341,7 @@ int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
     }
     p.ntile = ntile; p.nsplits = cout_pad / ntile; p.cout_pad = cout_pad; p.cout = cout;
     p.epilogue = epilogue; p.act = act; p.bias = bias; p.res = (const __half*)res; p.out = out;
-    p.out_cstride = out_cstride;
+    p.out_cstride = out_cstride; p.os = out_os;
     p.tiles_x = (OW + kTileW - 1) / kTileW;
     const int tiles_y = (OH + kTileH - 1) / kTileH;
 

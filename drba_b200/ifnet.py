@@ -70,7 +70,8 @@ def _pack_convT_phase(weight, py, px):
 class _TcLayer:
     """One conv layer packed for drba_conv_tc_f16: w[G][T][cout_pad][cin_pad] fp16, bias[G][cout_pad] fp32."""
 
-    def __init__(self, w, b, dy, dx, stride, act, cout, epilogue, device, cin_real=None):
+    def __init__(self, w, b, dy, dx, stride, act, cout, epilogue, device, cin_real=None, out_os=1):
+        self.out_os = out_os
         self.cin_real = cin_real if cin_real is not None else w.shape[3]
         self.w = w.to(torch.float16).contiguous().to(device)
         self.b = b.float().contiguous().to(device)
@@ -132,6 +133,23 @@ def _tc_lastconv(weight, bias, device):
     return _TcLayer(wp, bp, dys, dxs, 1, 0, cout, 1, device)
 
 
+def _tc_convT(weight, bias, device):
+    """ConvTranspose2d(cin, cout, 4, 2, 1) as four phase convs writing NHWC fp16 at (2y+py, 2x+px)."""
+    cin, cout = weight.shape[0], weight.shape[1]
+    cp = _pad16(cout)
+    wp = torch.zeros((4, 4, cp, cin))
+    bp = torch.zeros((4, cp))
+    dys, dxs = [], []
+    for py in (0, 1):
+        for px in (0, 1):
+            w, dy, dx = _pack_convT_phase(weight, py, px)
+            wp[py * 2 + px, :, :cout, :] = w.permute(0, 2, 1)
+            bp[py * 2 + px, :cout] = bias.float()
+            dys += dy
+            dxs += dx
+    return _TcLayer(wp, bp, dys, dxs, 1, 0, cout, 0, device, out_os=2)
+
+
 class IFNetEngine:
     def __init__(self, state, device, precision="fp32"):
         if precision not in ("fp32", "fp16"):
@@ -176,6 +194,9 @@ class IFNetEngine:
                     p = f"{name}.convblock.{i}"
                     self.tc[f"{name}.res{i}"] = _tc_conv3x3(sd[p + ".conv.weight"], sd[p + ".conv.bias"], 1, 1, d, sd[p + ".beta"])
                 self.tc[f"{name}.last"] = _tc_lastconv(sd[f"{name}.lastconv.0.weight"], sd[f"{name}.lastconv.0.bias"], d)
+            for i in (1, 2):
+                self.tc[f"encode.cnn{i}"] = _tc_conv3x3(sd[f"encode.cnn{i}.weight"], sd[f"encode.cnn{i}.bias"], 1, 1, d)
+            self.tc["encode.cnn3"] = _tc_convT(sd["encode.cnn3.weight"], sd["encode.cnn3.bias"], d)
         self.launches = 0   # kernels launched through this engine (bench.py reports it)
 
     # ------------------------------------------------------------------ helpers
@@ -204,12 +225,12 @@ class IFNetEngine:
                                                layer.act, stream_ptr(self.device))
         self._check(rc, "drba_conv2d_direct_f32")
 
-    def _conv_tc(self, layer, x, H, W, out, OH, OW, out_cstride, res=None):
+    def _conv_tc(self, layer, x, H, W, out, OH, OW, out_cstride, res=None, tag=""):
         # algorithmic FLOPs: real channels only (2 * Cin * Cout * taps * Hout * Wout)
-        with self._launch("conv_tc_f16", flops=2.0 * layer.G * layer.T * layer.cin_real * layer.cout * OH * OW):
+        with self._launch("conv_tc_f16" + (("/" + tag) if tag else ""), flops=2.0 * layer.G * layer.T * layer.cin_real * layer.cout * OH * OW):
             rc = self.L.drba_conv_tc_f16(ptr(x), H, W, layer.cin, ptr(layer.w), ptr(layer.b), layer.G, layer.T,
                                          layer.dy, layer.dx, layer.cout_pad, layer.cout, layer.stride, OH, OW,
-                                         layer.epilogue, layer.act, ptr(res), ptr(out), out_cstride, stream_ptr(self.device))
+                                         layer.epilogue, layer.act, ptr(res), ptr(out), out_cstride, layer.out_os, stream_ptr(self.device))
         self._check(rc, "drba_conv_tc_f16")
 
     @staticmethod
@@ -225,6 +246,19 @@ class IFNetEngine:
         _, _, H, W = img.shape
         assert H % 2 == 0 and W % 2 == 0
         h2, w2 = H // 2, W // 2
+        if self.precision == "fp16":
+            # first conv (Cin = 3) on CUDA cores straight into NHWC fp16, the rest on the tensor cores
+            f16 = torch.float16
+            a = self._buf(("enc_ah", H, W), (h2, w2, 16), f16)
+            b = self._buf(("enc_bh", H, W), (h2, w2, 16), f16)
+            feat = torch.empty((H, W, 16), dtype=f16, device=self.device)
+            with torch.cuda.device(self.device):
+                self._conv_direct(self.direct["encode.cnn0"], ptr(img), H, W, self._nchw(3, H, W), a, h2, w2,
+                                  (h2 * w2 * 16, 1, w2 * 16, 16))
+                self._conv_tc(self.tc["encode.cnn1"], a, h2, w2, b, h2, w2, 16, tag="encode.cnn12")
+                self._conv_tc(self.tc["encode.cnn2"], b, h2, w2, a, h2, w2, 16, tag="encode.cnn12")
+                self._conv_tc(self.tc["encode.cnn3"], a, h2, w2, feat, h2, w2, 16, tag="encode.cnn3")
+            return feat
         a = self._buf(("enc_a", H, W), (16, h2, w2))
         b = self._buf(("enc_b", H, W), (16, h2, w2))
         feat = torch.empty((H, W, 16), dtype=torch.float16 if self.precision == "fp16" else torch.float32,
@@ -263,16 +297,16 @@ class IFNetEngine:
             x = self._buf(("xh", bi, H, W), (h, w, cin_pad), f16)
             self._assemble(x, 1, cin_pad, img0, img1, f0, f1, timestep, ts_scalar, flow, prev, H, W, s)
             a = self._buf(("ah", bi, H, W), (h2, w2, c // 2), f16)
-            self._conv_tc(self.tc[f"{name}.conv0a"], x, h, w, a, h2, w2, c // 2)
+            self._conv_tc(self.tc[f"{name}.conv0a"], x, h, w, a, h2, w2, c // 2, tag=f"{name}.conv0a")
             p0 = self._buf(("p0h", bi, H, W), (h4, w4, c), f16)
             p1 = self._buf(("p1h", bi, H, W), (h4, w4, c), f16)
-            self._conv_tc(self.tc[f"{name}.conv0b"], a, h2, w2, p0, h4, w4, c)
+            self._conv_tc(self.tc[f"{name}.conv0b"], a, h2, w2, p0, h4, w4, c, tag=f"{name}.conv0b")
             cur, nxt = p0, p1
             for i in range(8):
-                self._conv_tc(self.tc[f"{name}.res{i}"], cur, h4, w4, nxt, h4, w4, c, res=cur)
+                self._conv_tc(self.tc[f"{name}.res{i}"], cur, h4, w4, nxt, h4, w4, c, res=cur, tag=f"{name}.res")
                 cur, nxt = nxt, cur
             tmp = self._buf(("tmp13", bi, H, W), (h, w, 16), torch.float32)
-            self._conv_tc(self.tc[f"{name}.last"], cur, h4, w4, tmp, h4, w4, 16)
+            self._conv_tc(self.tc[f"{name}.last"], cur, h4, w4, tmp, h4, w4, 16, tag=f"{name}.last")
             return tmp, 1, s
         # exact engine: NCHW fp32 activations
         x = self._buf(("x", bi, H, W), (cin, h, w))

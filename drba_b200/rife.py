@@ -11,7 +11,13 @@ Differences a caller can observe (DESIGN.md "boundary"):
 * ``precision='fp32'`` (default here) computes everything in fp32; ``precision='fp16'`` runs the
   convolutions on the tensor cores with fp16 operands like the reference under torch.autocast
   (rife.py:26, :78); flows, DRM maps, warps and splats are fp32 in both;
-* only the DRM map the caller consumes is computed (rife.py:99 / :105 use one of the two).
+* only the DRM map the caller consumes is computed (rife.py:99 / :105 use one of the two);
+* ``graphs=True`` (default): each distinct window shape (frame size, timestamp list, with/without
+  ``reuse``) is captured once into a CUDA graph and replayed, which removes the ~150 kernel-launch
+  gaps per window.  Replays read static input buffers (inputs are copied in) and the returned
+  frames are copies of the graph's output buffers; the returned ``reuse`` tuple aliases graph
+  buffers that stay valid until the same window shape runs again (infer.py consumes it in the
+  very next window).
 """
 import os
 
@@ -26,7 +32,7 @@ from .weights import load_ifnet_state
 
 class RIFE:
     def __init__(self, weights='weights/train_log_rife_426_heavy', scale=1.0,
-                 device=None, precision="fp32", state=None):
+                 device=None, precision="fp32", state=None, graphs=True):
         if device is None:
             device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         device = torch.device(device)
@@ -42,6 +48,9 @@ class RIFE:
         self.scale = scale
         self.scale_list = [16 / scale, 8 / scale, 4 / scale, 2 / scale, 1 / scale]
         self.pad_size = 64
+        self.graphs = bool(graphs)
+        self._graphs = {}
+        self._capture_stream = None
 
     @torch.inference_mode()
     def inference_ts(self, I0, I1, ts):
@@ -71,6 +80,66 @@ class RIFE:
     @torch.inference_mode()
     def inference_ts_drba(self, I0, I1, I2, ts, reuse=None, linear=False):
         """models/rife.py:77-109."""
+        if self.graphs:
+            return self._drba_graphed(I0, I1, I2, ts, reuse, linear)
+        return self._drba_eager(I0, I1, I2, ts, reuse, linear)
+
+    def _drba_graphed(self, I0, I1, I2, ts, reuse, linear):
+        ts_key = tuple(float(t) for t in ts)
+        frames = (I0, I1, I2)
+        for f in frames:
+            if not f.is_cuda:
+                raise _lib.DrbaError("drba_b200.RIFE runs on CUDA tensors only (no CPU fallback)")
+        key = (tuple(I0.shape), ts_key, bool(reuse), bool(linear))
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._capture(key, frames, ts, reuse, linear)
+        s_in, s_reuse, graph, outs, new_reuse, passthrough, n_kernels = entry
+        for dst, src in zip(s_in, frames):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src.float())
+        if reuse:
+            for dst, src in zip(s_reuse, reuse):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src)
+        graph.replay()
+        _lib.count(n_kernels)      # kernels inside the replayed graph (recorded at capture)
+        output = []
+        for o, pt in zip(outs, passthrough):
+            output.append(frames[pt] if pt >= 0 else o.clone())   # t in {0,1,2}: the input tensor itself (rife.py:89-94)
+        return output, new_reuse
+
+    def _capture(self, key, frames, ts, reuse, linear):
+        dev = self.device
+        s_in = [torch.empty_like(f, dtype=torch.float32, memory_format=torch.contiguous_format) for f in frames]
+        s_reuse = [torch.empty_like(r) for r in reuse] if reuse else None
+        for dst, src in zip(s_in, frames):
+            dst.copy_(src)
+        if reuse:
+            for dst, src in zip(s_reuse, reuse):
+                dst.copy_(src)
+        if self._capture_stream is None:
+            self._capture_stream = torch.cuda.Stream(device=dev)
+        cs = self._capture_stream
+        cs.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cs):      # warm-up: allocates engine buffers / workspaces outside the capture
+            self._drba_eager(*s_in, ts, tuple(s_reuse) if reuse else None, linear)
+        torch.cuda.current_stream(dev).wait_stream(cs)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        k0 = _lib.KERNEL_LAUNCHES
+        with torch.cuda.graph(graph, stream=cs):
+            outs, new_reuse = self._drba_eager(*s_in, ts, tuple(s_reuse) if reuse else None, linear)
+        n_kernels = _lib.KERNEL_LAUNCHES - k0
+        _lib.count(-n_kernels)     # capture records, it does not execute
+        passthrough = []
+        for o in outs:
+            passthrough.append(next((k for k, si in enumerate(s_in) if o is si), -1))
+        entry = (s_in, s_reuse, graph, outs, new_reuse, passthrough, n_kernels)
+        self._graphs[key] = entry
+        return entry
+
+    def _drba_eager(self, I0, I1, I2, ts, reuse=None, linear=False):
         flow10, flow01, f1, f0 = self.calc_flow(I1, I0) if not reuse else reuse
         if reuse is None:
             flow12, flow21, f1, f2 = self.calc_flow(I1, I2)

@@ -145,15 +145,17 @@ DRBA_API int drba_conv2d_direct_f32(const float* in, const float* w, const float
  *   in   : NHWC fp16 [H][W][Cin], Cin % 16 == 0 (zero-padded channels)
  *   w    : fp16 [G][T][cout_pad][Cin];  bias: fp32 [G][cout_pad];  dy, dx: int [G][T] tap offsets
  *   out[oy][ox][co] = act(bias + res + sum_t sum_ci in[S*oy + dy[t]][S*ox + dx[t]][ci] * w[g][t][co][ci])
- *   epilogue 0: NHWC fp16 [OH][OW][out_cstride] (G must be 1), optional residual `res` of the
- *               same geometry, act 0 none / 1 LeakyReLU(0.2)
+ *   epilogue 0: NHWC fp16, optional residual `res` of the same geometry, act 0 none / 1 LeakyReLU(0.2)
+ *               out_os 1: [OH][OW][out_cstride], G = 1
+ *               out_os 2: ConvTranspose2d(k4,s2,p1) as G = 4 phase convs (g = py*2+px, T = 4):
+ *                         [2*OH][2*OW][out_cstride], phase g lands at (2*oy + py, 2*ox + px)  (Head.cnn3)
  *   epilogue 1: lastconv = ConvTranspose2d(Cin,52,4,2,1)+PixelShuffle(2): G = 4 phases (py*2+px),
  *               T = 4, cout_pad = 64, cout = 52; out = NHWC fp32 [4*OH][4*OW][16] (13 used)
  * ------------------------------------------------------------------------- */
 DRBA_API int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
                               const void* w, const float* bias, int G, int T, const int* dy, const int* dx,
                               int cout_pad, int cout, int S, int OH, int OW,
-                              int epilogue, int act, const void* res, void* out, int out_cstride, void* stream);
+                              int epilogue, int act, const void* res, void* out, int out_cstride, int out_os, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Fused non-conv stages of IFNet.forward (IFNet_HDv3.py:126-177), batch 1.
