@@ -27,8 +27,8 @@
 namespace drba {
 
 constexpr int kTcThreads = 192;
-constexpr int kTileW = 16, kTileH = 8, kTileM = 128;
-constexpr int kStages = 4;
+constexpr int kTileM = 128;
+constexpr int kMaxStages = 8;
 constexpr int kMaxNTile = 128;
 constexpr int kMaxTapsTc = 9;
 constexpr int kMaxGroups = 4;
@@ -52,6 +52,8 @@ struct TcParams {
     int out_cstride;        // channels per pixel in `out` (epilogue 0)
     int os;                 // epilogue 0: output placement stride; group g = phase (py, px) lands at (os*oy + py, os*ox + px)
     int tiles_x;
+    int tile_w, tile_h;     // pixel patch of one CTA: tile_w * tile_h = 128
+    int stages;             // smem pipeline depth (<= kMaxStages)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,16 +132,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int b_bytes = p.ntile * p.Kc * 2;
     const int b_off = a_bytes;                                   // a_bytes is a multiple of 1024 (Kc >= 16 -> 4096)
     const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
-    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
+    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar;
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-    const int oy0 = ty * kTileH, ox0 = tx * kTileW;
+    const int oy0 = ty * p.tile_h, ox0 = tx * p.tile_w;
+    const int kStages = p.stages;
     const int nsplit = blockIdx.y, g = blockIdx.z;
     const int KI = p.T * p.kchunks;
 
+    // let the next kernel in the stream start its prologue while this one runs (PDL)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
@@ -156,6 +161,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // everything above overlapped the previous kernel's tail; its results are visible after this
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -203,7 +210,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ===== epilogue: warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int oy = oy0 + row / kTileW, ox = ox0 + row % kTileW;
+        const int oy = oy0 + row / p.tile_w, ox = ox0 + row % p.tile_w;
         const bool valid = oy < p.OH && ox < p.OW;
         mbar_wait(&accum_bar, 0);
         tc_fence_after();
@@ -331,19 +338,29 @@ int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
     p.S = S; p.T = T;
     for (int gi = 0; gi < G; ++gi)
         for (int t = 0; t < T; ++t) { p.dy[gi][t] = dy[gi * T + t]; p.dx[gi][t] = dx[gi * T + t]; }
-    // N tile: <= 128 columns, a multiple of 16 that divides cout_pad
-    int ntile = cout_pad;
-    if (ntile > kMaxNTile) {
-        ntile = 0;
-        for (int cand = kMaxNTile; cand >= 16; cand -= 16)
-            if (cout_pad % cand == 0) { ntile = cand; break; }
-        if (!ntile) return DRBA_E_UNSUPPORTED;
+    // pixel patch of a CTA: the 128-pixel rectangle that covers the output with the fewest tiles
+    int best_tiles = 1 << 30;
+    p.tile_w = 16; p.tile_h = 8;
+    const int shapes[5][2] = {{16, 8}, {32, 4}, {8, 16}, {64, 2}, {128, 1}};
+    for (int i = 0; i < 5; ++i) {
+        const int nt = ((OW + shapes[i][0] - 1) / shapes[i][0]) * ((OH + shapes[i][1] - 1) / shapes[i][1]);
+        if (nt < best_tiles) { best_tiles = nt; p.tile_w = shapes[i][0]; p.tile_h = shapes[i][1]; }
+    }
+    p.tiles_x = (OW + p.tile_w - 1) / p.tile_w;
+    const int tiles_y = (OH + p.tile_h - 1) / p.tile_h;
+    const int tiles = p.tiles_x * tiles_y;
+    // N tile: <= 128 columns, a multiple of 16 that divides cout_pad; small layers are split further
+    // so that more SMs stream the K loop in parallel
+    int ntile = 0;
+    for (int cand = cout_pad < kMaxNTile ? cout_pad : kMaxNTile; cand >= 16; cand -= 16)
+        if (cout_pad % cand == 0) { ntile = cand; break; }
+    if (!ntile) return DRBA_E_UNSUPPORTED;
+    if (epilogue == 0) {
+        while (ntile >= 64 && ntile % 32 == 0 && tiles * G * (cout_pad / ntile) * 2 <= kNumSMs) ntile /= 2;
     }
     p.ntile = ntile; p.nsplits = cout_pad / ntile; p.cout_pad = cout_pad; p.cout = cout;
     p.epilogue = epilogue; p.act = act; p.bias = bias; p.res = (const __half*)res; p.out = out;
     p.out_cstride = out_cstride; p.os = out_os;
-    p.tiles_x = (OW + kTileW - 1) / kTileW;
-    const int tiles_y = (OH + kTileH - 1) / kTileH;
 
     // A: input viewed as [H/S][S][W/S][S][C], innermost first
     CUtensorMap ta, tb;
@@ -351,7 +368,7 @@ int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)S, (cuuint64_t)(W / S), (cuuint64_t)S, (cuuint64_t)(H / S)};
         const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)S * Cin * 2, (cuuint64_t)W * Cin * 2,
                                        (cuuint64_t)S * W * Cin * 2};
-        const cuuint32_t box[5] = {(cuuint32_t)p.Kc, 1, kTileW, 1, kTileH};
+        const cuuint32_t box[5] = {(cuuint32_t)p.Kc, 1, (cuuint32_t)p.tile_w, 1, (cuuint32_t)p.tile_h};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         const CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(in), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(p.swz_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -369,14 +386,35 @@ int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
         if (r != CUDA_SUCCESS) return DRBA_E_UNSUPPORTED;
     }
     const int a_bytes = kTileM * p.Kc * 2, b_bytes = ntile * p.Kc * 2;
-    const size_t smem = (size_t)kStages * (a_bytes + ((b_bytes + 1023) & ~1023)) + 1024;
+    const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+    // pipeline depth: a TMA round trip is ~1-2 us, so a CTA needs many stages in flight.  Few CTAs
+    // (latency-bound small layers): take the whole SM; many CTAs: leave room for 2-3 CTAs per SM.
+    const int ctas = tiles * p.nsplits * G;
+    const int budget = ctas <= kNumSMs ? 220 * 1024 : (ctas <= 2 * kNumSMs ? 108 * 1024 : 72 * 1024);
+    int stages = budget / stage_bytes;
+    const int KI = T * p.kchunks;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > KI) stages = KI;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         attr_set = true;
     }
-    dim3 grid(p.tiles_x * tiles_y, p.nsplits, G);
-    conv_tc_kernel<<<grid, kTcThreads, smem, as_stream(stream)>>>(ta, tb, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tiles, p.nsplits, G);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap our prologue with the previous kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, ta, tb, p);
+    if (le != cudaSuccess) return (int)le;
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
 }

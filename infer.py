@@ -1,0 +1,171 @@
+#!/usr/bin/env python
+"""DRBA command line, re-hosted on the B200 implementation of the hot path.
+
+Same flags and loop semantics as the reference's infer.py (:18-36 flags, :58-174 loop); the
+per-window work runs in libdrba_b200.so.  Only `-m rife` is served by this build (the GMFSS rows of
+SURVEY.md 8 are next); other model names raise like the reference's unknown-model branch.
+Extra flags: --precision {fp16,fp32} (conv engine), --weights DIR.
+"""
+import argparse
+import os
+import subprocess
+import shutil
+import sys
+import time
+from queue import Queue
+from threading import Thread
+
+import numpy as np
+
+
+def parse_args():
+    parser = argparse.ArgumentParser(description='Interpolation a video with DRBA')
+    parser.add_argument('-m', '--model_type', dest='model_type', type=str, default='rife',
+                        help='model network type, current support rife/gmfss/gmfss_union')
+    parser.add_argument('-i', '--input', dest='input', type=str, default='input.mp4', help='absolute path of input video')
+    parser.add_argument('-o', '--output', dest='output', type=str, default='output.mp4', help='absolute path of output video')
+    parser.add_argument('-fps', '--dst_fps', dest='dst_fps', type=float, default=60, help='interpolate to ? fps')
+    parser.add_argument('-t', '--times', dest='times', type=int, default=-1, help='interpolate to ?x fps')
+    parser.add_argument('-s', '--enable_scdet', dest='enable_scdet', action='store_true', default=False,
+                        help='enable scene change detection')
+    parser.add_argument('-st', '--scdet_threshold', dest='scdet_threshold', type=float, default=0.3,
+                        help='ssim scene detection threshold')
+    parser.add_argument('-hw', '--hwaccel', dest='hwaccel', action='store_true', default=False,
+                        help='enable hardware acceleration encode(require nvidia graph card)')
+    parser.add_argument('-scale', '--scale', dest='scale', type=float, default=1.0,
+                        help='flow scale, generally use 1.0 with 1080P and 0.5 with 4K resolution')
+    parser.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
+    parser.add_argument('--weights', default=None, help='directory holding flownet.pkl')
+    return parser.parse_args()
+
+
+def load_model(model_type, scale, device, precision, weights):
+    if model_type == 'rife':
+        from drba_b200.rife import RIFE
+        from drba_b200.weights import find_rife_weights
+        wdir = find_rife_weights(weights)
+        if wdir is None:
+            raise FileNotFoundError('weights/train_log_rife_426_heavy/flownet.pkl')
+        return RIFE(weights=wdir, scale=scale, device=device, precision=precision)
+    if model_type in ('gmfss', 'gmfss_union'):
+        raise NotImplementedError(f'{model_type}: not part of this build yet (SURVEY.md section 8, next rows)')
+    raise ValueError(f'model_type must in {model_type}')
+
+
+class VideoIO:
+    """models/utils/tools.py:156-213: cv2 decode thread + encoder thread.  The encoder is the
+    reference's ffmpeg rawvideo pipe when an ffmpeg binary exists, else cv2.VideoWriter."""
+
+    def __init__(self, input_path, output_path, dst_fps=60, times=-1, hwaccel=False):
+        import cv2
+        self.cv2 = cv2
+        self.cap = cv2.VideoCapture(input_path)
+        self.src_fps = self.cap.get(cv2.CAP_PROP_FPS)
+        self.dst_fps = dst_fps if times == -1 else times * self.src_fps
+        self.total_frames_count = self.cap.get(7)
+        self.width = int(self.cap.get(cv2.CAP_PROP_FRAME_WIDTH))
+        self.height = int(self.cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+        self.ffmpeg = None
+        self.writer = None
+        if shutil.which('ffmpeg'):
+            enc, preset = ('h264_nvenc', 'p7') if hwaccel else ('libx264', 'medium')
+            cmd = ['ffmpeg', '-y', '-f', 'rawvideo', '-pix_fmt', 'rgb24', '-r', f'{self.dst_fps}',
+                   '-s', f'{self.width}x{self.height}', '-i', 'pipe:0', '-i', input_path, '-map', '0:v', '-map', '1:a?',
+                   '-c:v', enc, '-movflags', '+faststart', '-pix_fmt', 'yuv420p', '-qp', '16', '-preset', preset,
+                   '-c:a', 'aac', '-b:a', '320k', f'{output_path}']
+            self.ffmpeg = subprocess.Popen(cmd, stdin=subprocess.PIPE)
+        else:
+            self.writer = cv2.VideoWriter(output_path, cv2.VideoWriter_fourcc(*'mp4v'), self.dst_fps, (self.width, self.height))
+        self.read_buffer = Queue(maxsize=100)
+        self.write_buffer = Queue(maxsize=-1)
+        self.done = False
+        Thread(target=self._read, daemon=True).start()
+        Thread(target=self._write, daemon=True).start()
+
+    def _read(self):
+        ret, x = self.cap.read()
+        while ret:
+            self.read_buffer.put(x)
+            ret, x = self.cap.read()
+        self.read_buffer.put(None)
+
+    def _write(self):
+        while True:
+            item = self.write_buffer.get()
+            if item is None:
+                break
+            if self.ffmpeg is not None:
+                self.ffmpeg.stdin.write(np.ascontiguousarray(item[:, :, ::-1]))   # BGR -> RGB only here (tools.py:202)
+            else:
+                self.writer.write(item)
+        if self.ffmpeg is not None:
+            self.ffmpeg.stdin.close()
+            self.ffmpeg.wait()
+        else:
+            self.writer.release()
+        self.done = True
+
+    def write_frame(self, x):
+        self.write_buffer.put(x)
+
+    def read_frame(self):
+        return self.read_buffer.get()
+
+    def finish(self):
+        self.write_buffer.put(None)
+        while not self.done:
+            time.sleep(0.05)
+
+
+def inference(args):
+    import torch
+    from drba_b200 import driver, tools
+    device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+    model = load_model(args.model_type, args.scale, device, args.precision, args.weights)
+    io = VideoIO(args.input, args.output, dst_fps=args.dst_fps, times=args.times, hwaccel=args.hwaccel)
+    if io.dst_fps <= io.src_fps:
+        raise ValueError(f'dst fps should be greater than src fps, but got dst_fps={io.dst_fps} and src_fps={io.src_fps}')
+    try:
+        from tqdm import tqdm
+        pbar = tqdm(total=io.total_frames_count)
+    except Exception:
+        pbar = None
+    i0, i1 = io.read_frame(), io.read_frame()
+    size = tools.get_valid_net_inp_size(i0, model.scale, div=model.pad_size)
+    src_size, dst_size = size['src_size'], size['dst_size']
+    calc_t = driver.make_calc_t(io.src_fps, io.dst_fps, args.times)
+    scene = (lambda a, b: tools.check_scene(a, b, args.scdet_threshold)) if args.enable_scdet else (lambda a, b: False)
+
+    def emit(frames):
+        for x in frames:
+            io.write_frame(tools.to_out(x, src_size))
+        if pbar is not None:
+            pbar.update(1)
+
+    I0, I1 = tools.to_inp(i0, dst_size, device), tools.to_inp(i1, dst_size, device)
+    idx = 0
+    left_scene = scene(I0, I1)
+    reuse = None
+    emit(driver.head_outputs(model, I0, I1, calc_t(idx), left_scene))
+    while True:
+        i2 = io.read_frame()
+        if i2 is None:
+            break
+        I2 = tools.to_inp(i2, dst_size, device)
+        right_scene = scene(I1, I2)
+        output, reuse = driver.window_outputs(model, I0, I1, I2, calc_t(idx), reuse, left_scene, right_scene)
+        emit(output)
+        I0, I1 = I1, I2
+        left_scene = right_scene
+        idx += 1
+    emit(driver.tail_outputs(model, I0, I1, calc_t(idx)))
+    io.finish()
+    if pbar is not None:
+        pbar.close()
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if not os.path.exists(a.input):
+        raise FileNotFoundError(f"can't find the video file {a.input}")
+    inference(a)
