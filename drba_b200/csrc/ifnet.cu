@@ -15,7 +15,7 @@
 //                   exist.  Output: channels [warp(img0) 3 | warp(img1) 3 | warp(f0) 16 |
 //                   warp(f1) 16 | timestep 1 | mask 1 | feat 8 | flow/s 4] (IFNet_HDv3.py:151-
 //                   155 + :87-88), NCHW fp32 (exact engine) or NHWC fp16 (tensor-core engine).
-//                   Four threads per output pixel (f0 | f1 | images | timestep,mask,feat,flow);
+//                   Four warps per 32 output pixels, one role each (f0 | f1 | images | timestep,mask,feat,flow);
 //                   mask/feat are bilinear taps of the previous block's small lastconv output
 //                   (L2 resident) -- a full-resolution mask/feat tensor is never written.
 //  ifnet_flow_accum: the only full-resolution state is the fp32 flow [H][W][4]:
@@ -298,8 +298,9 @@ template <typename FT, bool NHWC_HALF, int TMP_LAYOUT>
 __global__ void __launch_bounds__(kIfThreads)
 ifnet_assemble_kernel(const AssembleParams p)
 {
-    const int gid = blockIdx.x * kIfThreads + threadIdx.x;
-    const int idx = gid >> 2, role = gid & 3;
+    // one warp per role (no divergence inside a warp), one lane per output pixel
+    const int role = threadIdx.x >> 5;
+    const int idx = blockIdx.x * 32 + (threadIdx.x & 31);
     if (idx >= p.h * p.w) return;
     const bool first = p.flow == nullptr;
     if (first && role == 3) return;
@@ -407,7 +408,7 @@ int drba_ifnet_assemble(const float* img0, const float* img1, const void* f0, co
     p.timestep = timestep; p.timestep_scalar = timestep_scalar; p.flow = flow;
     p.prev.p = tmp_prev; p.prev.s = flow ? s_prev : 1; p.prev.h13 = flow ? H / s_prev : 1; p.prev.w13 = flow ? W / s_prev : 1;
     p.out = out; p.out_cstride = out_cstride; p.H = H; p.W = W; p.s = s; p.h = H / s; p.w = W / s;
-    const unsigned grid = cdiv((size_t)p.h * p.w * 4, kIfThreads);
+    const unsigned grid = cdiv((size_t)p.h * p.w, 32);
     cudaStream_t st = as_stream(stream);
     const int key = (feat_dtype == DRBA_F16 ? 4 : 0) | (out_dtype == DRBA_F16 ? 2 : 0) | (tmp_layout == 1 ? 1 : 0);
     switch (key) {
