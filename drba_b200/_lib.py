@@ -37,10 +37,23 @@ SIGNATURES = {
     "drba_conv2d_direct_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P,
                                     _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "drba_conv_tc_f16": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
+    "drba_conv_tc_program_f16": (_I, [_P, _I, _I, _P, _P]),
+    "drba_conv_tc_debug_trace": (_I, [_P]),
     "drba_ifnet_assemble": (_I, [_P, _P, _P, _P, _I, _P, _F, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
     "drba_ifnet_flow_accum": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P]),
     "drba_ifnet_blend": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P]),
 }
+
+
+class ConvLayer(ctypes.Structure):
+    """struct drba_conv_layer (include/drba_b200.h)."""
+    _fields_ = [("in_", _P * 2), ("res", _P * 2), ("out", _P * 2), ("w", _P), ("bias", _P), ("slope", _P),
+                ("H", _I), ("W", _I), ("Cin", _I), ("G", _I), ("T", _I), ("dy", _I * 36), ("dx", _I * 36),
+                ("cout_pad", _I), ("cout", _I), ("S", _I), ("OH", _I), ("OW", _I), ("epilogue", _I), ("act", _I),
+                ("out_cstride", _I), ("out_os", _I)]
+
+
+CONV_MAX_LAYERS = 12
 
 
 class DrbaError(RuntimeError):

@@ -1,59 +1,82 @@
-// tcgen05 implicit-GEMM convolution for sm_100a (fp16 operands, fp32 accumulation in TMEM).
+// tcgen05 implicit-GEMM convolution engine for sm_100a (fp16 operands, fp32 accumulation in TMEM).
 //
-// Serves every conv of IFNet 4.26-heavy's refinement blocks
-// (models/rife_426_heavy/IFNet_HDv3.py:62-96: conv0 (two 3x3 stride-2), 8 x ResConv (3x3),
-// lastconv ConvTranspose2d(c, 52, 4, 2, 1) + PixelShuffle(2)) in the reference's own GPU
-// precision (fp16 under torch.autocast, models/rife.py:26,78; accumulation fp32).
+// Serves every conv of IFNet 4.26-heavy (models/rife_426_heavy/IFNet_HDv3.py:28-96: Head, conv0
+// (two 3x3 stride-2), 8 x ResConv (3x3), lastconv ConvTranspose2d(c, 52, 4, 2, 1) + PixelShuffle(2))
+// in the reference's own GPU precision (fp16 under torch.autocast, models/rife.py:26,78).
 //
 // GEMM view: M = output pixels, N = output channels, K = taps x Cin.
-//  * activations are NHWC fp16; a CTA owns a 16 x 8 pixel patch (M tile = 128 rows) and an
-//    N tile of <= 128 channels; its accumulator is a [128 lanes x ntile columns] fp32 block
-//    of tensor memory;
-//  * per K step (one tap, Kc input channels) ONE tiled TMA load brings the shifted
-//    [8][16][Kc] window of the input into shared memory as a K-major, hardware-swizzled
-//    [128 x Kc] A tile -- zero padding comes from TMA's out-of-bounds fill, so there is no
-//    im2col buffer and no halo logic; a second TMA load brings the [ntile x Kc] weight tile.
-//    Stride-2 convs view the input as [H/2][2][W/2][2][C] (rank-5 tensor map) so that a tap
-//    is still a dense box;
-//  * warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer (+ TMEM alloc),
-//    warps 2-5 = epilogue (tcgen05.ld -> bias / residual / LeakyReLU -> fp16 NHWC store, or
-//    the lastconv pixel-shuffle scatter); smem stages are recycled through full/empty
-//    mbarriers, tcgen05.commit releases a stage when the MMAs reading it retire;
-//  * ConvTranspose(4,2,1) is four 2x2-tap phase convs (grid.z = phase), N = 52 padded to 64;
-//    the epilogue writes PixelShuffle(2)'d NHWC fp32 [4h][4w][16] directly.
+//  * activations are NHWC fp16; a tile is a 128-pixel rectangle (16x8, 32x4, ...) times an N tile of
+//    <= 128 channels; its accumulator is a [128 lanes x ntile columns] fp32 block of tensor memory;
+//  * per K step ONE tiled TMA load brings the shifted [th][tw][Kc] window of the input into shared
+//    memory as a K-major, hardware-swizzled [128 x Kc] A tile -- zero padding is TMA out-of-bounds
+//    fill, so there is no im2col buffer and no halo logic; a second TMA load brings the weight tile.
+//    Stride-2 convs view the input as [H/2][2][W/2][2][C] (rank-5 tensor map) so a tap stays a dense
+//    box.  Layers with few input channels put several taps into one pipeline stage.
+//  * ConvTranspose(4,2,1) is four 2x2-tap phase convs; the lastconv epilogue writes the
+//    PixelShuffle(2)'d NHWC fp32 [4h][4w][16] directly.
+//
+// Execution model: ONE PERSISTENT LAUNCH RUNS A PROGRAM OF LAYERS.  Measured on B200, a 128-pixel
+// tile costs more in CTA start-up (barrier init, TMEM allocation, descriptor fetch, drain) than in
+// MMA or TMA time, and the coarse IFNet levels (510 ... 8160 pixels) are pure launch latency.  So:
+//  * grid = min(tiles, 148) CTAs, one per SM; each CTA walks its tiles of the current layer with a
+//    shared-memory ring that never drains between tiles;
+//  * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-5 / 6-9 = two epilogue groups that
+//    alternate tiles over a double-buffered TMEM accumulator (the epilogue of tile i overlaps the
+//    main loop of tile i+1);
+//  * consecutive layers (a whole IFBlock: conv0a, conv0b, 8 x ResConv, lastconv) are chained inside
+//    the launch with a grid-wide barrier (release/acquire counter in global memory) instead of a
+//    kernel boundary; up to two independent images (the two interpolated frames of a DRBA window)
+//    share the launch and the weights.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace drba {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;        // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
 constexpr int kTileM = 128;
-constexpr int kMaxStages = 8;
+constexpr int kStages = 6;
+constexpr int kABytesMax = 16384;      // 128 rows x 128 B
+constexpr int kStageBytes = 32768;     // A (<= 16 KB) | B (<= 16 KB)
 constexpr int kMaxNTile = 128;
 constexpr int kMaxTapsTc = 9;
 constexpr int kMaxGroups = 4;
-constexpr int kTmemCols = 128;
+constexpr int kTmemCols = 256;         // two accumulators of <= 128 columns
+constexpr int kMaxLayers = DRBA_CONV_MAX_LAYERS;
+constexpr int kMaxImages = 2;
 
-struct TcParams {
-    int OH, OW;             // output grid (per group)
-    int Cin, Kc, kchunks;   // input channels (padded), channels per K step, Cin / Kc
-    int S;                  // input stride (1 or 2)
-    int T;                  // taps per group
-    int dy[kMaxGroups][kMaxTapsTc], dx[kMaxGroups][kMaxTapsTc];
-    int ntile, nsplits;     // N tile and number of N tiles per group
-    int cout_pad;           // weight rows per (group, tap)
-    int cout;               // real output channels per group
-    int swz_bytes;          // 32 / 64 / 128
-    int epilogue;           // 0: NHWC fp16 (+res, act); 1: lastconv pixel shuffle -> fp32 [4*OH][4*OW][16]
-    int act;                // 0 none, 1 LeakyReLU(0.2)
+struct alignas(64) LayerDev {
+    CUtensorMap ta[kMaxImages];
+    CUtensorMap tb;
     const float* bias;      // [G][cout_pad]
-    const __half* res;      // NHWC fp16, same geometry as out (or NULL)
-    void* out;
-    int out_cstride;        // channels per pixel in `out` (epilogue 0)
-    int os;                 // epilogue 0: output placement stride; group g = phase (py, px) lands at (os*oy + py, os*ox + px)
-    int tiles_x;
-    int tile_w, tile_h;     // pixel patch of one CTA: tile_w * tile_h = 128
-    int stages;             // smem pipeline depth (<= kMaxStages)
+    const float* slope;     // PReLU slopes [cout_pad] (act 2) or NULL
+    const __half* res[kMaxImages];
+    void* out[kMaxImages];
+    int OH, OW;
+    int Kc, kchunks;        // channels per K step, Cin / Kc
+    int S, T, G;
+    int tps;                // taps per pipeline stage (> 1 only when kchunks == 1)
+    int KI;                 // pipeline iterations per tile
+    int ntile, nsplits, cout_pad, cout;
+    int swz_bytes;          // 32 / 64 / 128
+    int a_sub, b_sub;       // byte stride between the taps of one stage
+    int epilogue;           // 0: NHWC fp16 (+res, act); 1: lastconv pixel shuffle -> fp32 [4*OH][4*OW][16]
+    int act;                // 0 none, 1 LeakyReLU(0.2), 2 PReLU(slope), 3 ReLU
+    int out_cstride, os;
+    int tiles_x, mtiles, tile_w, tile_h;
+    int total_tiles;        // nimg * G * nsplits * mtiles
+    // per (group, tap): cell offset y | cell offset x << 8 | parity y << 16 | parity x << 17 (offsets biased by +64)
+    int tapc[kMaxGroups][kMaxTapsTc + 3];
+};
+
+struct Program {
+    int nlayers, nimg;
+    unsigned* sync;         // [2] grid-barrier arrival counter, exit counter (zero between launches)
+    int dbg;
+    int pad_;
+    long long* trace;       // debug: clock64 stamps of CTA 0 (NULL in production)
+    LayerDev L[kMaxLayers];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,6 +86,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -74,17 +100,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar,
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
                                             int c0, int c1, int c2, int c3, int c4) {
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
                  " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                  : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
                  " [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -98,18 +124,15 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-// 16 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
+// 16 consecutive fp32 columns of this thread's TMEM lane (no wait: pair with tc_ld_wait)
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 |
@@ -120,36 +143,88 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int swz_bytes) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
-__device__ __forceinline__ float lrelu02(float v) { return v > 0.0f ? v : 0.2f * v; }
+// one lane of a converged warp, chosen by the hardware: keeps the surrounding control flow warp-uniform so
+// that TMA / MMA operands stay in uniform registers (a plain `lane == 0` branch makes the compiler
+// wrap every UTMALDG / UTCHMMA in an R2UR waterfall loop, ~150 cycles per instruction)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "elect.sync _|p, 0xffffffff;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(pred));
+    return pred != 0;
+}
+
+struct TileCoord { int img, g, nsplit, oy0, ox0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const LayerDev& L, int idx) {
+    TileCoord t;
+    const int m = idx % L.mtiles;
+    int r = idx / L.mtiles;
+    t.nsplit = r % L.nsplits; r /= L.nsplits;
+    t.g = r % L.G;
+    t.img = r / L.G;
+    const int ty = m / L.tiles_x, tx = m - ty * L.tiles_x;
+    t.oy0 = ty * L.tile_h;
+    t.ox0 = tx * L.tile_w;
+    return t;
+}
+
+__device__ __forceinline__ float activate(float v, int act, float slope) {
+    if (act == 1) return v > 0.0f ? v : 0.2f * v;
+    if (act == 2) return v > 0.0f ? v : slope * v;
+    if (act == 3) return v > 0.0f ? v : 0.0f;
+    return v;
+}
+
+// grid-wide barrier between two layers of a program: every CTA arrives once per layer
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    unsigned v;
+    unsigned spins = 0;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target && ++spins < (1u << 24));   // bail out instead of hanging the GPU if a CTA is missing
+}
+
+#define TC_TRACE(slot) do { if (trace && blockIdx.x == 0) trace[(slot)] = clock64(); } while (0)
+
+constexpr int kTapTabStride = 12;
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p)
+conv_tc_kernel(const __grid_constant__ Program prog)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: stages x (A tile | B tile), 1024-byte aligned, then barriers
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int a_bytes = kTileM * p.Kc * 2;
-    const int b_bytes = p.ntile * p.Kc * 2;
-    const int b_off = a_bytes;                                   // a_bytes is a multiple of 1024 (Kc >= 16 -> 4096)
-    const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
-    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar;
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float s_bias[kMaxGroups * 128 > 512 ? kMaxGroups * 128 : 512];
+    __shared__ __align__(16) float s_slope[512];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-    const int oy0 = ty * p.tile_h, ox0 = tx * p.tile_w;
-    const int kStages = p.stages;
-    const int nsplit = blockIdx.y, g = blockIdx.z;
-    const int KI = p.T * p.kchunks;
+    long long* const trace = prog.trace;
+    const int dbg = prog.dbg;
+    const int nlayers = prog.nlayers;
+
+    // per-layer tables (tap geometry, bias, PReLU slopes) live in shared memory: the layer descriptors sit
+    // in kernel-parameter space and are indexed dynamically, which makes every field access a slow
+    // generic load -- the single-thread producer / MMA loops must not touch them per iteration
+    auto stage_tables = [&](int li) {
+        const LayerDev& L = prog.L[li];
+        const int nb = L.G * L.cout_pad;
+        for (int i = threadIdx.x; i < nb; i += kTcThreads) s_bias[i] = L.bias[i];
+        if (L.act == 2)
+            for (int i = threadIdx.x; i < L.cout_pad; i += kTcThreads) s_slope[i] = L.slope[i];
+    };
 
     // let the next kernel in the stream start its prologue while this one runs (PDL)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) TC_TRACE(4090);
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[0].ta[0]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[0].tb) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&accum_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -157,129 +232,265 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                      ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    stage_tables(0);           // weights / bias are never written by a preceding kernel: safe before griddepcontrol.wait
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     // everything above overlapped the previous kernel's tail; its results are visible after this
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) TC_TRACE(4091);
 
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            for (int it = 0; it < KI; ++it) {
-                const int s = it % kStages, ph = (it / kStages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + b_bytes));
-                const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                const int dy = p.dy[g][tap], dx = p.dx[g][tap];
-                // input coordinate = S * o + d  ->  (parity, cell) in the [H/S][S][W/S][S][C] view
-                int pary = 0, parx = 0, cy = oy0 + dy, cx = ox0 + dx;
-                if (p.S == 2) {
-                    pary = dy & 1; parx = dx & 1;
-                    cy = oy0 + ((dy - pary) >> 1); cx = ox0 + ((dx - parx) >> 1);
-                }
-                uint8_t* sa = smem + (size_t)s * stage_bytes;
-                tma_load_5d(sa, &tmap_a, &full_bar[s], kc * p.Kc, parx, cx, pary, cy);
-                tma_load_2d(sa + b_off, &tmap_b, &full_bar[s], kc * p.Kc,
-                            (g * p.T + tap) * p.cout_pad + nsplit * p.ntile);
+    uint32_t stage = 0, phase = 0;   // smem ring position (producer and MMA thread keep their own copy)
+    uint32_t tcount = 0;             // tiles this CTA has started so far (MMA thread and epilogue warps keep their own copy)
+
+    for (int li = 0; li < nlayers; ++li) {
+        const LayerDev& L = prog.L[li];
+        // layer constants -> registers (once per layer)
+        const int total_tiles = L.total_tiles, mtiles = L.mtiles, nsplits = L.nsplits, G = L.G;
+        const int tiles_x = L.tiles_x, tile_w = L.tile_w, tile_h = L.tile_h;
+        const int KI = L.KI, tps = L.tps, T = L.T, ntile = L.ntile;
+
+        if (warp == 0) {
+            // ===== TMA producer: the whole warp walks the loop, one elected lane issues =====
+            const int Kc = L.Kc, kchunks = L.kchunks, cout_pad = L.cout_pad;
+            const uint32_t a_sub = L.a_sub, b_sub = L.b_sub;
+            const uint32_t tap_bytes = (uint32_t)(((dbg & 2) ? 0 : kTileM * Kc * 2) + ((dbg & 4) ? 0 : ntile * Kc * 2));
+            if (li + 1 < nlayers && elect_one()) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].ta[0]) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].tb) : "memory");
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
+            const CUtensorMap* tb = &L.tb;
+            for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x) {
+                const int m = idx % mtiles;
+                int r = idx / mtiles;
+                const int nsplit = r % nsplits; r /= nsplits;
+                const int g = r % G, img = r / G;
+                const int ty = m / tiles_x;
+                const int oy0 = ty * tile_h, ox0 = (m - ty * tiles_x) * tile_w;
+                const CUtensorMap* ta = &L.ta[img];
+                const int brow0 = g * T * cout_pad + nsplit * ntile;
+                int tap = 0, kc = 0;
+                for (int it = 0; it < KI; ++it) {
+                    if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 0);
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    const int ntaps = tps > 1 ? min(tps, T - tap) : 1;
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)ntaps * tap_bytes);
+                        const uint32_t sa = smem + stage * kStageBytes;
+                        for (int u = 0; u < ntaps; ++u) {
+                            const int e = L.tapc[g][tap + u];
+                            const int cy = (e & 0xff) - 64, cx = ((e >> 8) & 0xff) - 64, pary = (e >> 16) & 1, parx = (e >> 17) & 1;
+                            if (!(dbg & 2)) tma_load_5d(sa + u * a_sub, ta, &full_bar[stage], kc * Kc, parx, ox0 + cx, pary, oy0 + cy);
+                            if (!(dbg & 4)) tma_load_2d(sa + kABytesMax + u * b_sub, tb, &full_bar[stage], kc * Kc, brow0 + (tap + u) * cout_pad);
+                        }
+                    }
+                    __syncwarp();
+                    if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 1);
+                    if (tps > 1) tap += ntaps;
+                    else if (++kc == kchunks) { kc = 0; ++tap; }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer: whole warp in the loop, one elected lane issues =====
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, K-major both,
             // N >> 3 at [17,23), M >> 4 at [24,29)
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-            const int ksteps = p.Kc >> 4;
-            for (int it = 0; it < KI; ++it) {
-                const int s = it % kStages, ph = (it / kStages) & 1;
-                mbar_wait(&full_bar[s], ph);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(ntile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const int ksteps = (dbg & 1) ? 0 : (L.Kc >> 4);
+            const uint32_t a_sub16 = (uint32_t)L.a_sub >> 4, b_sub16 = (uint32_t)L.b_sub >> 4;
+            const uint64_t desc_hi = make_desc(0, L.swz_bytes);
+            for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount) {
+                const uint32_t buf = tcount & 1u, use = tcount >> 1;
+                mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);     // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t da = make_desc(sa, p.swz_bytes), db = make_desc(sa + b_off, p.swz_bytes);
-                for (int k = 0; k < ksteps; ++k) {
-                    // advance 16 fp16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
-                    tc_mma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                const uint32_t tmem_d = tmem_base + buf * (uint32_t)kMaxNTile;
+                uint32_t accumulate = 0;
+                int tap = 0;
+                for (int it = 0; it < KI; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 2);
+                    const int ntaps = tps > 1 ? min(tps, T - tap) : 1;
+                    tap += ntaps;
+                    const uint32_t sa16 = ((smem + stage * kStageBytes) & 0x3FFFFu) >> 4;
+                    if (elect_one()) {
+                        for (int u = 0; u < ntaps; ++u) {
+                            const uint64_t da = desc_hi | (uint64_t)(sa16 + u * a_sub16);
+                            const uint64_t db = desc_hi | (uint64_t)(sa16 + (kABytesMax >> 4) + u * b_sub16);
+                            for (int k = 0; k < ksteps; ++k) {
+                                // advance 16 fp16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
+                                tc_mma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)(u | k));
+                            }
+                        }
+                        tc_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    accumulate = 1;
+                    if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 3);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(&empty_bar[s]);
+                if (elect_one()) tc_commit(&acc_full[buf]);
+                __syncwarp();
             }
-            tc_commit(&accum_bar);
-        }
-    } else {
-        // ===== epilogue: warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int oy = oy0 + row / p.tile_w, ox = ox0 + row % p.tile_w;
-        const bool valid = oy < p.OH && ox < p.OW;
-        mbar_wait(&accum_bar, 0);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float* bias = p.bias + (size_t)g * p.cout_pad + nsplit * p.ntile;
-        if (p.epilogue == 0) {
-            const size_t pix = p.os == 1 ? (size_t)oy * p.OW + ox
-                                         : (size_t)(oy * p.os + (g >> 1)) * (p.OW * p.os) + (ox * p.os + (g & 1));
-            __half* out = reinterpret_cast<__half*>(p.out) + pix * p.out_cstride + nsplit * p.ntile;
-            const __half* res = p.res ? p.res + pix * p.out_cstride + nsplit * p.ntile : nullptr;
-            for (int c0 = 0; c0 < p.ntile; c0 += 16) {
-                float v[16];
-                tc_ld16(taddr + c0, v);
-                if (!valid) continue;
-                if (nsplit * p.ntile + c0 >= p.cout) continue;
+        } else {
+            // ===== epilogue: group 0 = warps 2..5, group 1 = warps 6..9; a warp may only touch TMEM
+            // lanes 32*(warp%4) .. +31 =====
+            const uint32_t group = (uint32_t)(warp - 2) >> 2;
+            const int q = warp & 3;
+            const int row = q * 32 + lane;
+            const int ry = row / tile_w, rx = row - ry * tile_w;
+            const int OH = L.OH, OW = L.OW, cout = L.cout, cout_pad = L.cout_pad, act = L.act;
+            const int epilogue = L.epilogue, os = L.os, cstride = L.out_cstride;
+            for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount) {
+                const uint32_t buf = tcount & 1u, use = tcount >> 1;
+                if (buf != group) continue;
+                const int m = idx % mtiles;
+                int r = idx / mtiles;
+                const int nsplit = r % nsplits; r /= nsplits;
+                const int g = r % G, img = r / G;
+                const int ty = m / tiles_x;
+                const int oy = ty * tile_h + ry, ox = (m - ty * tiles_x) * tile_w + rx;
+                const bool valid = oy < OH && ox < OW;
+                const int nbase = nsplit * ntile;
+                const float* bias = s_bias + g * cout_pad + nbase;
+                const uint32_t taddr = tmem_base + buf * (uint32_t)kMaxNTile + ((uint32_t)(q * 32) << 16);
+                if (epilogue == 0) {
+                    const size_t pix = os == 1 ? (size_t)oy * OW + ox
+                                               : (size_t)(oy * os + (g >> 1)) * (OW * os) + (ox * os + (g & 1));
+                    __half* out = reinterpret_cast<__half*>(L.out[img]) + pix * cstride + nbase;
+                    const __half* resb = L.res[img];
+                    const __half* res = (resb && valid) ? resb + pix * cstride + nbase : nullptr;
+                    // the residual does not depend on the accumulator: fetch (up to) 64 channels before waiting
+                    uint4 rpre[8];
+                    if (res) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += __ldg(bias + c0 + i);
-                if (res) {
-                    const uint4* r4 = reinterpret_cast<const uint4*>(res + c0);
+                        for (int h = 0; h < 8; ++h)
+                            if (h * 8 < ntile) rpre[h] = reinterpret_cast<const uint4*>(res)[h];
+                    }
+                    mbar_wait(&acc_full[buf], use & 1u);
+                    tc_fence_after();
+                    if (idx == blockIdx.x && q == 2 && lane == 0) TC_TRACE(li * 256 + 200);
+                    for (int c0 = 0; c0 < ntile; c0 += 32) {
+                        uint32_t rr[32];
+                        tc_ld16_nowait(taddr + c0, rr);
+                        if (c0 + 16 < ntile) tc_ld16_nowait(taddr + c0 + 16, rr + 16);
+                        tc_ld_wait();
+                        if (!valid) continue;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint4 rr = r4[h];
-                        const __half2* hh = reinterpret_cast<const __half2*>(&rr);
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int c = c0 + hh * 16;
+                            if (c >= ntile || nbase + c >= cout) continue;
+                            float v[16];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float2 f = __half22float2(hh[k]);
-                            v[h * 8 + k * 2] += f.x; v[h * 8 + k * 2 + 1] += f.y;
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(bias + c + i);
+                                v[i] = __uint_as_float(rr[hh * 16 + i]) + b4.x;
+                                v[i + 1] = __uint_as_float(rr[hh * 16 + i + 1]) + b4.y;
+                                v[i + 2] = __uint_as_float(rr[hh * 16 + i + 2]) + b4.z;
+                                v[i + 3] = __uint_as_float(rr[hh * 16 + i + 3]) + b4.w;
+                            }
+                            if (res) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    uint4 rv;
+                                    if (c0 == 0) rv = rpre[hh * 2 + h];
+                                    else if (c0 == 32) rv = rpre[4 + hh * 2 + h];
+                                    else rv = reinterpret_cast<const uint4*>(res + c)[h];
+                                    const __half2* hp = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const float2 f = __half22float2(hp[k]);
+                                        v[h * 8 + k * 2] += f.x; v[h * 8 + k * 2 + 1] += f.y;
+                                    }
+                                }
+                            }
+                            if (act == 1) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.0f ? v[i] : 0.2f * v[i];
+                            } else if (act == 2) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.0f ? v[i] : s_slope[nbase + c + i] * v[i];
+                            } else if (act == 3) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+                            }
+                            uint4 o[2];
+                            __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) oh[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                            uint4* o4 = reinterpret_cast<uint4*>(out + c);
+                            o4[0] = o[0]; o4[1] = o[1];
+                        }
+                    }
+                } else {
+                    // lastconv: group g = phase (py, px); channel co = c13*4 + i*2 + j lands at
+                    // out[4*oy + 2*py + i][4*ox + 2*px + j][c13]  (ConvTranspose phase + PixelShuffle(2))
+                    const int py = g >> 1, px = g & 1;
+                    const int OW4 = OW * 4;
+                    float* out = reinterpret_cast<float*>(L.out[img]);
+                    mbar_wait(&acc_full[buf], use & 1u);
+                    tc_fence_after();
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t rr[32];
+                        tc_ld16_nowait(taddr + c0, rr);
+                        tc_ld16_nowait(taddr + c0 + 16, rr + 16);
+                        tc_ld_wait();
+                        if (!valid) continue;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int c = c0 + hh * 16;
+                            float v[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[hh * 16 + i]) + bias[c + i];
+#pragma unroll
+                            for (int ij = 0; ij < 4; ++ij) {
+                                const int yy = 4 * oy + 2 * py + (ij >> 1), xx = 4 * ox + 2 * px + (ij & 1);
+                                const float4 o = make_float4(v[0 + ij], v[4 + ij], v[8 + ij], v[12 + ij]);
+                                *reinterpret_cast<float4*>(out + ((size_t)yy * OW4 + xx) * 16 + (c >> 2)) = o;
+                            }
                         }
                     }
                 }
-                if (p.act == 1) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = lrelu02(v[i]);
-                }
-                uint4 o[2];
-                __half2* oh = reinterpret_cast<__half2*>(o);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) oh[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-                uint4* o4 = reinterpret_cast<uint4*>(out + c0);
-                o4[0] = o[0]; o4[1] = o[1];
-            }
-        } else {
-            // lastconv: group g = phase (py, px); channel co = c13*4 + i*2 + j lands at
-            // out[4*oy + 2*py + i][4*ox + 2*px + j][c13]  (ConvTranspose phase + PixelShuffle(2))
-            const int py = g >> 1, px = g & 1;
-            const int OW4 = p.OW * 4;
-            float* out = reinterpret_cast<float*>(p.out);
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-                float v[16];
-                tc_ld16(taddr + c0, v);
-                if (!valid) continue;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += __ldg(bias + c0 + i);
-#pragma unroll
-                for (int ij = 0; ij < 4; ++ij) {
-                    const int yy = 4 * oy + 2 * py + (ij >> 1), xx = 4 * ox + 2 * px + (ij & 1);
-                    float4 o = make_float4(v[0 + ij], v[4 + ij], v[8 + ij], v[12 + ij]);
-                    *reinterpret_cast<float4*>(out + ((size_t)yy * OW4 + xx) * 16 + (c0 >> 2)) = o;
-                }
+                if (idx == blockIdx.x && q == 2 && lane == 0) TC_TRACE(li * 256 + 201);
+                // accumulator drained: hand the buffer back to the MMA thread
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
             }
         }
-        tc_fence_before();
+
+        if (li + 1 < nlayers) {
+            // layer boundary: this layer's outputs (generic-proxy stores) must be visible to every CTA's
+            // TMA loads (async proxy) of the next layer
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) { TC_TRACE(li * 256 + 202); grid_barrier(prog.sync, (unsigned)(li + 1) * gridDim.x); TC_TRACE(li * 256 + 203); }
+            stage_tables(li + 1);
+            __syncthreads();
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
     }
+
+    tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TC_TRACE(4092);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
     }
+    if (nlayers > 1 && threadIdx.x == 0) {
+        // the last CTA to leave re-zeroes the barrier state for the next launch
+        const unsigned old = atomicAdd(prog.sync + 1, 1u);
+        if (old == gridDim.x - 1) {
+            prog.sync[0] = 0u;
+            prog.sync[1] = 0u;
+            __threadfence();
+        }
+    }
 }
+
 
 // ---- host side ---------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -304,107 +515,157 @@ static CUtensorMapSwizzle swz_enum(int bytes)
     return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTiledFn encode)
+{
+    const int H = d.H, W = d.W, Cin = d.Cin, G = d.G, T = d.T, S = d.S, OH = d.OH, OW = d.OW;
+    if (!d.w || !d.bias) return DRBA_E_ARG;
+    if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || Cin <= 0 || Cin % 16 != 0) return DRBA_E_ARG;
+    if (G < 1 || G > kMaxGroups || T < 1 || T > kMaxTapsTc) return DRBA_E_ARG;
+    if (S != 1 && S != 2) return DRBA_E_ARG;
+    if (S == 2 && (H % 2 != 0 || W % 2 != 0)) return DRBA_E_ARG;
+    if (d.cout_pad <= 0 || d.cout_pad % 16 != 0 || d.cout <= 0 || d.cout > d.cout_pad) return DRBA_E_ARG;
+    if (d.epilogue != 0 && d.epilogue != 1) return DRBA_E_ARG;
+    if (d.epilogue == 1 && (d.cout_pad != 64 || d.cout != 52 || G != 4)) return DRBA_E_ARG;
+    if (d.out_os != 1 && d.out_os != 2) return DRBA_E_ARG;
+    if (d.epilogue == 0 && ((d.out_os == 1 && G != 1) || (d.out_os == 2 && G != 4))) return DRBA_E_ARG;
+    if (d.epilogue == 0 && (d.out_cstride < d.cout_pad || d.out_cstride % 8 != 0)) return DRBA_E_ARG;
+    if (d.act < 0 || d.act > 3 || (d.act == 2 && !d.slope)) return DRBA_E_ARG;
+    if (G * d.cout_pad > 512) return DRBA_E_UNSUPPORTED;   // bias / slope tables staged in shared memory
+    if (!aligned16(d.w)) return DRBA_E_ALIGN;
+    for (int i = 0; i < nimg; ++i) {
+        if (!d.in[i] || !d.out[i]) return DRBA_E_ARG;
+        if (!aligned16(d.in[i]) || !aligned16(d.out[i]) || (d.res[i] && !aligned16(d.res[i]))) return DRBA_E_ALIGN;
+    }
+
+    memset(&L, 0, sizeof(L));
+    L.OH = OH; L.OW = OW; L.S = S; L.T = T; L.G = G;
+    L.Kc = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16);
+    L.kchunks = Cin / L.Kc;
+    L.swz_bytes = L.Kc * 2;
+    for (int gi = 0; gi < G; ++gi)
+        for (int t = 0; t < T; ++t) {
+            const int dy = d.dy[gi * T + t], dx = d.dx[gi * T + t];
+            if (dy < -32 || dy > 32 || dx < -32 || dx > 32) return DRBA_E_ARG;
+            int cy = dy, cx = dx, pary = 0, parx = 0;
+            // input coordinate = S * o + d  ->  (parity, cell) in the [H/S][S][W/S][S][C] view
+            if (S == 2) { pary = dy & 1; parx = dx & 1; cy = (dy - pary) >> 1; cx = (dx - parx) >> 1; }
+            L.tapc[gi][t] = (cy + 64) | ((cx + 64) << 8) | (pary << 16) | (parx << 17);
+        }
+    // pixel patch of a tile: the 128-pixel rectangle that covers the output with the fewest tiles
+    int best_tiles = 1 << 30;
+    L.tile_w = 16; L.tile_h = 8;
+    const int shapes[5][2] = {{16, 8}, {32, 4}, {8, 16}, {64, 2}, {128, 1}};
+    for (int i = 0; i < 5; ++i) {
+        const int nt = ((OW + shapes[i][0] - 1) / shapes[i][0]) * ((OH + shapes[i][1] - 1) / shapes[i][1]);
+        if (nt < best_tiles) { best_tiles = nt; L.tile_w = shapes[i][0]; L.tile_h = shapes[i][1]; }
+    }
+    L.tiles_x = (OW + L.tile_w - 1) / L.tile_w;
+    L.mtiles = L.tiles_x * ((OH + L.tile_h - 1) / L.tile_h);
+    // N tile: <= 128 columns, a multiple of 16 that divides cout_pad; small layers are split further
+    // so that more SMs stream the K loop in parallel
+    int ntile = 0;
+    for (int cand = d.cout_pad < kMaxNTile ? d.cout_pad : kMaxNTile; cand >= 16; cand -= 16)
+        if (d.cout_pad % cand == 0) { ntile = cand; break; }
+    if (!ntile) return DRBA_E_UNSUPPORTED;
+    if (d.epilogue == 0) {
+        while (ntile >= 64 && ntile % 32 == 0 && nimg * L.mtiles * G * (d.cout_pad / ntile) * 2 <= kNumSMs) ntile /= 2;
+    }
+    L.ntile = ntile; L.nsplits = d.cout_pad / ntile; L.cout_pad = d.cout_pad; L.cout = d.cout;
+    L.total_tiles = nimg * G * L.nsplits * L.mtiles;
+    L.epilogue = d.epilogue; L.act = d.act; L.bias = d.bias; L.slope = d.slope;
+    L.out_cstride = d.out_cstride; L.os = d.out_os;
+    for (int i = 0; i < nimg; ++i) { L.res[i] = (const __half*)d.res[i]; L.out[i] = d.out[i]; }
+
+    // taps per stage: thin layers (one K chunk per tap) put several taps behind one barrier so that a
+    // stage carries ~16 KB of activations
+    const int a_bytes = kTileM * L.Kc * 2, b_bytes = ntile * L.Kc * 2;
+    const int swz_period = 8 * L.swz_bytes;
+    L.a_sub = a_bytes;                                            // 4096 / 8192 / 16384: multiples of every period
+    L.b_sub = (b_bytes + swz_period - 1) / swz_period * swz_period;
+    L.tps = 1;
+    if (L.kchunks == 1) {
+        int tps = kABytesMax / a_bytes;
+        while (tps > 1 && tps * L.b_sub > kStageBytes - kABytesMax) --tps;
+        if (tps > T) tps = T;
+        // balance: e.g. 9 taps with room for 4 -> 3 stages of 3
+        const int iters = (T + tps - 1) / tps;
+        tps = (T + iters - 1) / iters;
+        L.tps = tps;
+    }
+    L.KI = L.tps > 1 ? (T + L.tps - 1) / L.tps : T * L.kchunks;
+    if (L.b_sub * L.tps > kStageBytes - kABytesMax) return DRBA_E_UNSUPPORTED;
+
+    // A: input viewed as [H/S][S][W/S][S][C], innermost first
+    for (int i = 0; i < nimg; ++i) {
+        const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)S, (cuuint64_t)(W / S), (cuuint64_t)S, (cuuint64_t)(H / S)};
+        const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)S * Cin * 2, (cuuint64_t)W * Cin * 2,
+                                       (cuuint64_t)S * W * Cin * 2};
+        const cuuint32_t box[5] = {(cuuint32_t)L.Kc, 1, (cuuint32_t)L.tile_w, 1, (cuuint32_t)L.tile_h};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const CUresult r = encode(&L.ta[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d.in[i]), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(L.swz_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return DRBA_E_UNSUPPORTED;
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)G * T * d.cout_pad};
+        const cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)L.Kc, (cuuint32_t)ntile};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&L.tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d.w), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(L.swz_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return DRBA_E_UNSUPPORTED;
+    }
+    return DRBA_OK;
+}
+
+static long long* g_trace = nullptr;
+
 }  // namespace drba
 
 using namespace drba;
 
 extern "C" {
 
-int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
-                     const void* w, const float* bias, int G, int T, const int* dy, const int* dx,
-                     int cout_pad, int cout, int S, int OH, int OW,
-                     int epilogue, int act, const void* res, void* out, int out_cstride, int out_os, void* stream)
+int drba_conv_tc_debug_trace(void* dev_buf_4096_i64)
 {
-    if (!in || !w || !bias || !out || !dy || !dx) return DRBA_E_ARG;
-    if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || Cin <= 0 || Cin % 16 != 0) return DRBA_E_ARG;
-    if (G < 1 || G > kMaxGroups || T < 1 || T > kMaxTapsTc) return DRBA_E_ARG;
-    if (S != 1 && S != 2) return DRBA_E_ARG;
-    if (S == 2 && (H % 2 != 0 || W % 2 != 0)) return DRBA_E_ARG;
-    if (cout_pad <= 0 || cout_pad % 16 != 0 || cout <= 0 || cout > cout_pad) return DRBA_E_ARG;
-    if (epilogue != 0 && epilogue != 1) return DRBA_E_ARG;
-    if (epilogue == 1 && (cout_pad != 64 || cout != 52 || G != 4)) return DRBA_E_ARG;
-    if (out_os != 1 && out_os != 2) return DRBA_E_ARG;
-    if (epilogue == 0 && ((out_os == 1 && G != 1) || (out_os == 2 && G != 4))) return DRBA_E_ARG;
-    if (epilogue == 0 && (out_cstride < cout_pad || out_cstride % 8 != 0)) return DRBA_E_ARG;
-    if (!aligned16(in) || !aligned16(w) || !aligned16(out) || (res && !aligned16(res))) return DRBA_E_ALIGN;
+    g_trace = (long long*)dev_buf_4096_i64;
+    return DRBA_OK;
+}
+
+int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nimg, void* sync_ws, void* stream)
+{
+    if (!layers || nlayers < 1 || nlayers > kMaxLayers || nimg < 1 || nimg > kMaxImages) return DRBA_E_ARG;
+    if (nlayers > 1 && (!sync_ws || (reinterpret_cast<uintptr_t>(sync_ws) & 7u))) return DRBA_E_WORKSPACE;
     EncodeTiledFn encode = get_encode();
     if (!encode) return DRBA_E_UNSUPPORTED;
 
-    TcParams p;
-    p.OH = OH; p.OW = OW; p.Cin = Cin;
-    p.Kc = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16);
-    p.kchunks = Cin / p.Kc;
-    p.swz_bytes = p.Kc * 2;
-    p.S = S; p.T = T;
-    for (int gi = 0; gi < G; ++gi)
-        for (int t = 0; t < T; ++t) { p.dy[gi][t] = dy[gi * T + t]; p.dx[gi][t] = dx[gi * T + t]; }
-    // pixel patch of a CTA: the 128-pixel rectangle that covers the output with the fewest tiles
-    int best_tiles = 1 << 30;
-    p.tile_w = 16; p.tile_h = 8;
-    const int shapes[5][2] = {{16, 8}, {32, 4}, {8, 16}, {64, 2}, {128, 1}};
-    for (int i = 0; i < 5; ++i) {
-        const int nt = ((OW + shapes[i][0] - 1) / shapes[i][0]) * ((OH + shapes[i][1] - 1) / shapes[i][1]);
-        if (nt < best_tiles) { best_tiles = nt; p.tile_w = shapes[i][0]; p.tile_h = shapes[i][1]; }
+    static int env_pdl = -1, env_dbg = -1, env_grid = -1;
+    if (env_pdl < 0) {
+        const char* e = getenv("DRBA_TC_PDL"); env_pdl = e ? atoi(e) : 1;
+        e = getenv("DRBA_TC_DBG"); env_dbg = e ? atoi(e) : 0;
+        e = getenv("DRBA_TC_GRID"); env_grid = e ? atoi(e) : 0;
     }
-    p.tiles_x = (OW + p.tile_w - 1) / p.tile_w;
-    const int tiles_y = (OH + p.tile_h - 1) / p.tile_h;
-    const int tiles = p.tiles_x * tiles_y;
-    // N tile: <= 128 columns, a multiple of 16 that divides cout_pad; small layers are split further
-    // so that more SMs stream the K loop in parallel
-    int ntile = 0;
-    for (int cand = cout_pad < kMaxNTile ? cout_pad : kMaxNTile; cand >= 16; cand -= 16)
-        if (cout_pad % cand == 0) { ntile = cand; break; }
-    if (!ntile) return DRBA_E_UNSUPPORTED;
-    if (epilogue == 0) {
-        while (ntile >= 64 && ntile % 32 == 0 && tiles * G * (cout_pad / ntile) * 2 <= kNumSMs) ntile /= 2;
+    Program prog;
+    prog.nlayers = nlayers; prog.nimg = nimg; prog.sync = (unsigned*)sync_ws; prog.dbg = env_dbg; prog.pad_ = 0;
+    prog.trace = g_trace;
+    int max_tiles = 0;
+    for (int i = 0; i < nlayers; ++i) {
+        const int rc = build_layer(layers[i], nimg, prog.L[i], encode);
+        if (rc != DRBA_OK) return rc;
+        if (prog.L[i].total_tiles > max_tiles) max_tiles = prog.L[i].total_tiles;
     }
-    p.ntile = ntile; p.nsplits = cout_pad / ntile; p.cout_pad = cout_pad; p.cout = cout;
-    p.epilogue = epilogue; p.act = act; p.bias = bias; p.res = (const __half*)res; p.out = out;
-    p.out_cstride = out_cstride; p.os = out_os;
-
-    // A: input viewed as [H/S][S][W/S][S][C], innermost first
-    CUtensorMap ta, tb;
-    {
-        const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)S, (cuuint64_t)(W / S), (cuuint64_t)S, (cuuint64_t)(H / S)};
-        const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)S * Cin * 2, (cuuint64_t)W * Cin * 2,
-                                       (cuuint64_t)S * W * Cin * 2};
-        const cuuint32_t box[5] = {(cuuint32_t)p.Kc, 1, (cuuint32_t)p.tile_w, 1, (cuuint32_t)p.tile_h};
-        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        const CUresult r = encode(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(in), dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(p.swz_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return DRBA_E_UNSUPPORTED;
-    }
-    {
-        const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)G * T * cout_pad};
-        const cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
-        const cuuint32_t box[2] = {(cuuint32_t)p.Kc, (cuuint32_t)ntile};
-        const cuuint32_t estr[2] = {1, 1};
-        const CUresult r = encode(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(p.swz_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return DRBA_E_UNSUPPORTED;
-    }
-    const int a_bytes = kTileM * p.Kc * 2, b_bytes = ntile * p.Kc * 2;
-    const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
-    // pipeline depth: a TMA round trip is ~1-2 us, so a CTA needs many stages in flight.  Few CTAs
-    // (latency-bound small layers): take the whole SM; many CTAs: leave room for 2-3 CTAs per SM.
-    const int ctas = tiles * p.nsplits * G;
-    const int budget = ctas <= kNumSMs ? 220 * 1024 : (ctas <= 2 * kNumSMs ? 108 * 1024 : 72 * 1024);
-    int stages = budget / stage_bytes;
-    const int KI = T * p.kchunks;
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages > KI) stages = KI;
-    if (stages < 2) stages = 2;
-    p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
+    if (env_grid > 0 && env_grid < grid) grid = env_grid;
     static bool attr_set = false;
+    const size_t smem = (size_t)kStages * kStageBytes + 1024;
     if (!attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(tiles, p.nsplits, G);
+    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = as_stream(stream);
@@ -412,11 +673,29 @@ int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap our prologue with the previous kernel
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, ta, tb, p);
+    cfg.numAttrs = env_pdl ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, prog);
     if (le != cudaSuccess) return (int)le;
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
+}
+
+int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
+                     const void* w, const float* bias, int G, int T, const int* dy, const int* dx,
+                     int cout_pad, int cout, int S, int OH, int OW,
+                     int epilogue, int act, const void* res, void* out, int out_cstride, int out_os, void* stream)
+{
+    if (!in || !w || !bias || !out || !dy || !dx) return DRBA_E_ARG;
+    if (G < 1 || G > kMaxGroups || T < 1 || T > kMaxTapsTc) return DRBA_E_ARG;
+    drba_conv_layer d;
+    memset(&d, 0, sizeof(d));
+    d.in[0] = in; d.res[0] = res; d.out[0] = out;
+    d.H = H; d.W = W; d.Cin = Cin; d.w = w; d.bias = bias; d.slope = nullptr;
+    d.G = G; d.T = T;
+    for (int i = 0; i < G * T; ++i) { d.dy[i] = dy[i]; d.dx[i] = dx[i]; }
+    d.cout_pad = cout_pad; d.cout = cout; d.S = S; d.OH = OH; d.OW = OW;
+    d.epilogue = epilogue; d.act = act; d.out_cstride = out_cstride; d.out_os = out_os;
+    return drba_conv_tc_program_f16(&d, 1, 1, nullptr, stream);
 }
 
 }  // extern "C"

@@ -82,6 +82,7 @@ class _TcLayer:
         self.stride = stride
         self.act = act
         self.epilogue = epilogue
+        self.slope = None
 
 
 def _pad16(n):
@@ -198,6 +199,7 @@ class IFNetEngine:
                 self.tc[f"encode.cnn{i}"] = _tc_conv3x3(sd[f"encode.cnn{i}.weight"], sd[f"encode.cnn{i}.bias"], 1, 1, d)
             self.tc["encode.cnn3"] = _tc_convT(sd["encode.cnn3.weight"], sd["encode.cnn3.bias"], d)
         self.launches = 0   # kernels launched through this engine (bench.py reports it)
+        self._sync = None   # grid-barrier words of the persistent conv programs
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, key, shape, dtype=torch.float32):
@@ -233,6 +235,32 @@ class IFNetEngine:
                                          layer.epilogue, layer.act, ptr(res), ptr(out), out_cstride, layer.out_os, stream_ptr(self.device))
         self._check(rc, "drba_conv_tc_f16")
 
+    def _conv_program(self, steps, tag=""):
+        """One persistent launch for a chain of tensor-core conv layers (drba_conv_tc_program_f16).
+        steps: [(layer, H, W, ins, outs, OH, OW, out_cstride, ress)] with ins/outs/ress lists of one tensor
+        per image (ress may be None); layer i+1 may read what layer i wrote."""
+        nimg = len(steps[0][3])
+        arr = (_lib.ConvLayer * len(steps))()
+        flops = 0.0
+        for c, (layer, H, W, ins, outs, OH, OW, cstride, ress) in zip(arr, steps):
+            for k in range(nimg):
+                c.in_[k] = ptr(ins[k])
+                c.out[k] = ptr(outs[k])
+                c.res[k] = ptr(ress[k]) if ress is not None else None
+            c.w, c.bias, c.slope = ptr(layer.w), ptr(layer.b), ptr(layer.slope)
+            c.H, c.W, c.Cin, c.G, c.T = H, W, layer.cin, layer.G, layer.T
+            n = layer.G * layer.T
+            c.dy[:n] = layer.dy[:n]
+            c.dx[:n] = layer.dx[:n]
+            c.cout_pad, c.cout, c.S, c.OH, c.OW = layer.cout_pad, layer.cout, layer.stride, OH, OW
+            c.epilogue, c.act, c.out_cstride, c.out_os = layer.epilogue, layer.act, cstride, layer.out_os
+            flops += nimg * 2.0 * layer.G * layer.T * layer.cin_real * layer.cout * OH * OW
+        if self._sync is None:
+            self._sync = torch.zeros(2, dtype=torch.int32, device=self.device)
+        with self._launch("conv_tc_f16" + (("/" + tag) if tag else ""), flops=flops):
+            rc = self.L.drba_conv_tc_program_f16(ctypes.addressof(arr), len(steps), nimg, ptr(self._sync), stream_ptr(self.device))
+        self._check(rc, "drba_conv_tc_program_f16")
+
     @staticmethod
     def _nchw(c, h, w):
         return (c * h * w, h * w, w, 1)
@@ -255,14 +283,13 @@ class IFNetEngine:
             with torch.cuda.device(self.device):
                 self._conv_direct(self.direct["encode.cnn0"], ptr(img), H, W, self._nchw(3, H, W), a, h2, w2,
                                   (h2 * w2 * 16, 1, w2 * 16, 16))
-                self._conv_tc(self.tc["encode.cnn1"], a, h2, w2, b, h2, w2, 16, tag="encode.cnn12")
-                self._conv_tc(self.tc["encode.cnn2"], b, h2, w2, a, h2, w2, 16, tag="encode.cnn12")
-                self._conv_tc(self.tc["encode.cnn3"], a, h2, w2, feat, h2, w2, 16, tag="encode.cnn3")
+                self._conv_program([(self.tc["encode.cnn1"], h2, w2, [a], [b], h2, w2, 16, None),
+                                    (self.tc["encode.cnn2"], h2, w2, [b], [a], h2, w2, 16, None),
+                                    (self.tc["encode.cnn3"], h2, w2, [a], [feat], h2, w2, 16, None)], tag="encode")
             return feat
         a = self._buf(("enc_a", H, W), (16, h2, w2))
         b = self._buf(("enc_b", H, W), (16, h2, w2))
-        feat = torch.empty((H, W, 16), dtype=torch.float16 if self.precision == "fp16" else torch.float32,
-                           device=self.device)
+        feat = torch.empty((H, W, 16), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._conv_direct(self.direct["encode.cnn0"], ptr(img), H, W, self._nchw(3, H, W), a, h2, w2, self._nchw(16, h2, w2))
             self._conv_direct(self.direct["encode.cnn1"], ptr(a), h2, w2, self._nchw(16, h2, w2), b, h2, w2, self._nchw(16, h2, w2))
@@ -284,49 +311,56 @@ class IFNetEngine:
                                             ptr(out), out_dtype, cstride, H, W, s, stream_ptr(self.device))
         self._check(rc, "drba_ifnet_assemble")
 
-    def _block(self, bi, img0, img1, f0, f1, timestep, ts_scalar, flow, prev, H, W, s):
-        """Runs block `bi`; returns (tmp, layout, s): its lastconv output (13 ch at 1/s)."""
+    def _block(self, bi, jobs, H, W, s):
+        """Runs block `bi` for every job (one job = one image pair: dict with img0, img1, f0, f1, ts_t, ts_s,
+        flow, prev); returns per job (tmp, layout, s): the block's lastconv output (13 ch at 1/s).
+        Tensor-core engine: one assemble per job, then ONE persistent conv program for all jobs."""
         name, cin, c = _BLOCKS[bi]
         h, w = H // s, W // s
         assert H % (4 * s) == 0 and W % (4 * s) == 0, "frame size must be a multiple of 4 * scale"
         h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
         if self.precision == "fp16":
-            # tensor-core engine: NHWC fp16 activations, 11 conv launches
             f16 = torch.float16
             cin_pad = 48 if bi == 0 else 64
-            x = self._buf(("xh", bi, H, W), (h, w, cin_pad), f16)
-            self._assemble(x, 1, cin_pad, img0, img1, f0, f1, timestep, ts_scalar, flow, prev, H, W, s)
-            a = self._buf(("ah", bi, H, W), (h2, w2, c // 2), f16)
-            self._conv_tc(self.tc[f"{name}.conv0a"], x, h, w, a, h2, w2, c // 2, tag=f"{name}.conv0a")
-            p0 = self._buf(("p0h", bi, H, W), (h4, w4, c), f16)
-            p1 = self._buf(("p1h", bi, H, W), (h4, w4, c), f16)
-            self._conv_tc(self.tc[f"{name}.conv0b"], a, h2, w2, p0, h4, w4, c, tag=f"{name}.conv0b")
+            nj = len(jobs)
+            xs = [self._buf(("xh", bi, H, W, k), (h, w, cin_pad), f16) for k in range(nj)]
+            for k, j in enumerate(jobs):
+                self._assemble(xs[k], 1, cin_pad, j["img0"], j["img1"], j["f0"], j["f1"], j["ts_t"], j["ts_s"], j["flow"], j["prev"], H, W, s)
+            a = [self._buf(("ah", bi, H, W, k), (h2, w2, c // 2), f16) for k in range(nj)]
+            p0 = [self._buf(("p0h", bi, H, W, k), (h4, w4, c), f16) for k in range(nj)]
+            p1 = [self._buf(("p1h", bi, H, W, k), (h4, w4, c), f16) for k in range(nj)]
+            tmp = [self._buf(("tmp13", bi, H, W, k), (h, w, 16), torch.float32) for k in range(nj)]
+            steps = [(self.tc[f"{name}.conv0a"], h, w, xs, a, h2, w2, c // 2, None),
+                     (self.tc[f"{name}.conv0b"], h2, w2, a, p0, h4, w4, c, None)]
             cur, nxt = p0, p1
             for i in range(8):
-                self._conv_tc(self.tc[f"{name}.res{i}"], cur, h4, w4, nxt, h4, w4, c, res=cur, tag=f"{name}.res")
+                steps.append((self.tc[f"{name}.res{i}"], h4, w4, cur, nxt, h4, w4, c, cur))
                 cur, nxt = nxt, cur
-            tmp = self._buf(("tmp13", bi, H, W), (h, w, 16), torch.float32)
-            self._conv_tc(self.tc[f"{name}.last"], cur, h4, w4, tmp, h4, w4, 16, tag=f"{name}.last")
-            return tmp, 1, s
+            steps.append((self.tc[f"{name}.last"], h4, w4, cur, tmp, h4, w4, 16, None))
+            self._conv_program(steps, tag=name)
+            return [(t, 1, s) for t in tmp]
         # exact engine: NCHW fp32 activations
-        x = self._buf(("x", bi, H, W), (cin, h, w))
-        self._assemble(x, 0, 0, img0, img1, f0, f1, timestep, ts_scalar, flow, prev, H, W, s)
-        a = self._buf(("a", bi, H, W), (c // 2, h2, w2))
-        self._conv_direct(self.direct[f"{name}.conv0a"], ptr(x), h, w, self._nchw(cin, h, w), a, h2, w2, self._nchw(c // 2, h2, w2))
-        p0 = self._buf(("p0", bi, H, W), (c, h4, w4))
-        p1 = self._buf(("p1", bi, H, W), (c, h4, w4))
-        st4 = self._nchw(c, h4, w4)
-        self._conv_direct(self.direct[f"{name}.conv0b"], ptr(a), h2, w2, self._nchw(c // 2, h2, w2), p0, h4, w4, st4)
-        cur, nxt = p0, p1
-        for i in range(8):
-            self._conv_direct(self.direct[f"{name}.res{i}"], ptr(cur), h4, w4, st4, nxt, h4, w4, st4, res_ptr=ptr(cur))
-            cur, nxt = nxt, cur
-        ct = self._buf(("ct", bi, H, W), (52, h2, w2))
-        for py in (0, 1):
-            for px in (0, 1):
-                self._conv_direct(self.direct[f"{name}.last{py}{px}"], ptr(cur), h4, w4, st4, ct, h4, w4,
-                                  self._nchw(52, h2, w2), OS=2, PY=py, PX=px)
-        return ct, 0, s
+        outs = []
+        for k, j in enumerate(jobs):
+            x = self._buf(("x", bi, H, W, k), (cin, h, w))
+            self._assemble(x, 0, 0, j["img0"], j["img1"], j["f0"], j["f1"], j["ts_t"], j["ts_s"], j["flow"], j["prev"], H, W, s)
+            a = self._buf(("a", bi, H, W), (c // 2, h2, w2))
+            self._conv_direct(self.direct[f"{name}.conv0a"], ptr(x), h, w, self._nchw(cin, h, w), a, h2, w2, self._nchw(c // 2, h2, w2))
+            p0 = self._buf(("p0", bi, H, W), (c, h4, w4))
+            p1 = self._buf(("p1", bi, H, W), (c, h4, w4))
+            st4 = self._nchw(c, h4, w4)
+            self._conv_direct(self.direct[f"{name}.conv0b"], ptr(a), h2, w2, self._nchw(c // 2, h2, w2), p0, h4, w4, st4)
+            cur, nxt = p0, p1
+            for i in range(8):
+                self._conv_direct(self.direct[f"{name}.res{i}"], ptr(cur), h4, w4, st4, nxt, h4, w4, st4, res_ptr=ptr(cur))
+                cur, nxt = nxt, cur
+            ct = self._buf(("ct", bi, H, W, k), (52, h2, w2))
+            for py in (0, 1):
+                for px in (0, 1):
+                    self._conv_direct(self.direct[f"{name}.last{py}{px}"], ptr(cur), h4, w4, st4, ct, h4, w4,
+                                      self._nchw(52, h2, w2), OS=2, PY=py, PX=px)
+            outs.append((ct, 0, s))
+        return outs
 
     def _flow_accum(self, prev, flow, planar, accumulate, H, W):
         tmp, layout, s = prev
@@ -344,29 +378,56 @@ class IFNetEngine:
         return si
 
     # ------------------------------------------------------------------ IFNet.forward (IFNet_HDv3.py:126-177)
+    MAX_BATCH = 2   # images per persistent conv program (include/drba_b200.h: drba_conv_layer)
+
+    def forward_multi(self, reqs, scale_list):
+        """IFNet.forward for several independent requests of the same frame size, run side by side
+        (they share every conv launch and the weights).  reqs: [(img0, img1, timestep, f0, f1)];
+        timestep is a float or a [1,1,H,W] tensor; f0/f1 from encode() or None.  Returns the frames."""
+        outs = []
+        for i in range(0, len(reqs), self.MAX_BATCH):
+            outs += self._forward_batch(reqs[i:i + self.MAX_BATCH], scale_list)
+        return outs
+
+    def _forward_batch(self, reqs, scale_list):
+        jobs = []
+        H = W = None
+        for k, (img0, img1, timestep, f0, f1) in enumerate(reqs):
+            require_cuda(img0, img1)
+            img0, img1 = img0.float().contiguous(), img1.float().contiguous()
+            if H is None:
+                _, _, H, W = img0.shape
+            elif tuple(img0.shape[2:]) != (H, W):
+                raise _lib.DrbaError("forward_multi needs frames of one size")
+            ts_t, ts_s = (timestep.float().contiguous(), 0.0) if torch.is_tensor(timestep) else (None, float(timestep))
+            jobs.append({"img0": img0, "img1": img1, "ts_t": ts_t, "ts_s": ts_s, "f0": f0, "f1": f1, "prev": None, "flow": None})
+        with torch.cuda.device(self.device):
+            for k, j in enumerate(jobs):
+                j["f0"] = self.encode(j["img0"]) if j["f0"] is None else j["f0"]
+                j["f1"] = self.encode(j["img1"]) if j["f1"] is None else j["f1"]
+                j["flow"] = self._buf(("flow", H, W, k), (H, W, 4))
+            for bi in range(5):
+                if bi > 0:     # flow (+)= s * up(previous lastconv[0:4])
+                    for j in jobs:
+                        self._flow_accum(j["prev"], j["flow"], None, bi > 1, H, W)
+                prevs = self._block(bi, jobs, H, W, self._int_scale(scale_list[bi]))
+                for j, p in zip(jobs, prevs):
+                    j["prev"] = p
+            outs = []
+            for j in jobs:
+                out = torch.empty((1, 3, H, W), dtype=torch.float32, device=self.device)
+                tmp, layout, s = j["prev"]
+                with self._launch("ifnet_blend", nbytes=float(H * W * (16 + 24 + 12))):
+                    rc = self.L.drba_ifnet_blend(ptr(j["img0"]), ptr(j["img1"]), ptr(j["flow"]), ptr(tmp), layout, s, ptr(out), H, W,
+                                                 stream_ptr(self.device))
+                self._check(rc, "drba_ifnet_blend")
+                outs.append(out)
+        return outs
+
     def forward(self, img0, img1, timestep, scale_list, f0=None, f1=None):
         """img0, img1 [1,3,H,W] fp32; timestep float or [1,1,H,W] tensor; f0/f1 from encode().
         Returns the interpolated frame [1,3,H,W] fp32 (merged[4] of the reference)."""
-        require_cuda(img0, img1)
-        img0, img1 = img0.float().contiguous(), img1.float().contiguous()
-        _, _, H, W = img0.shape
-        ts_t, ts_s = (timestep.float().contiguous(), 0.0) if torch.is_tensor(timestep) else (None, float(timestep))
-        with torch.cuda.device(self.device):
-            f0 = self.encode(img0) if f0 is None else f0
-            f1 = self.encode(img1) if f1 is None else f1
-            flow = self._buf(("flow", H, W), (H, W, 4))
-            prev = None
-            for bi in range(5):
-                if bi > 0:     # flow (+)= s * up(previous lastconv[0:4])
-                    self._flow_accum(prev, flow, None, bi > 1, H, W)
-                prev = self._block(bi, img0, img1, f0, f1, ts_t, ts_s, flow, prev, H, W, self._int_scale(scale_list[bi]))
-            out = torch.empty((1, 3, H, W), dtype=torch.float32, device=self.device)
-            tmp, layout, s = prev
-            with self._launch("ifnet_blend", nbytes=float(H * W * (16 + 24 + 12))):
-                rc = self.L.drba_ifnet_blend(ptr(img0), ptr(img1), ptr(flow), ptr(tmp), layout, s, ptr(out), H, W,
-                                             stream_ptr(self.device))
-            self._check(rc, "drba_ifnet_blend")
-        return out
+        return self._forward_batch([(img0, img1, timestep, f0, f1)], scale_list)[0]
 
     def block0_flow(self, img0, img1, f0, f1, timestep, scale):
         """ifnet.block0(cat(a, b, f0, f1, timestep), None, scale)[0] (models/rife.py:45-46): [1,4,H,W]."""
@@ -374,7 +435,8 @@ class IFNetEngine:
         img0, img1 = img0.float().contiguous(), img1.float().contiguous()
         _, _, H, W = img0.shape
         with torch.cuda.device(self.device):
-            prev = self._block(0, img0, img1, f0, f1, None, float(timestep), None, None, H, W, self._int_scale(scale))
+            job = {"img0": img0, "img1": img1, "ts_t": None, "ts_s": float(timestep), "f0": f0, "f1": f1, "prev": None, "flow": None}
+            prev = self._block(0, [job], H, W, self._int_scale(scale))[0]
             flow = torch.empty((1, 4, H, W), dtype=torch.float32, device=self.device)
             self._flow_accum(prev, None, flow, False, H, W)
         return flow

@@ -146,7 +146,9 @@ class RIFE:
         else:
             flow12, flow21, f1, f2 = self.calc_flow(I1, I2, f0=reuse[2])
 
-        output = list()
+        # the interpolated frames of a window are independent given the flows: collect them and run
+        # IFNet side by side (shared conv launches), then put the results back in `ts` order
+        output, reqs, slots = list(), list(), list()
         for t in ts:
             if t == 0:
                 output.append(I0)
@@ -157,13 +159,18 @@ class RIFE:
             elif 0 < t < 1:
                 t = 1 - t
                 drm = calc_drm_rife(t, flow10, flow12, linear, only='drm_t1_t01')
-                out = self.ifnet.forward(I1, I0, drm['drm_t1_t01'], self.scale_list, f0=f1, f1=f0)
-                output.append(out)
+                reqs.append((I1, I0, drm['drm_t1_t01'], f1, f0))
+                slots.append(len(output))
+                output.append(None)
             elif 1 < t < 2:
                 t = t - 1
                 drm = calc_drm_rife(t, flow10, flow12, linear, only='drm_t1_t12')
-                out = self.ifnet.forward(I1, I2, drm['drm_t1_t12'], self.scale_list, f0=f1, f1=f2)
-                output.append(out)
+                reqs.append((I1, I2, drm['drm_t1_t12'], f1, f2))
+                slots.append(len(output))
+                output.append(None)
+        if reqs:
+            for k, out in zip(slots, self.ifnet.forward_multi(reqs, self.scale_list)):
+                output[k] = out
 
         # next flow10, flow01 = reverse(current flow12, flow21)
         return output, (flow21, flow12, f2, f1)

@@ -157,6 +157,31 @@ DRBA_API int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
                               int cout_pad, int cout, int S, int OH, int OW,
                               int epilogue, int act, const void* res, void* out, int out_cstride, int out_os, void* stream);
 
+/* A program of conv layers executed by ONE persistent launch (csrc/conv_tc.cu): layer i+1 starts
+ * after a grid-wide barrier, so layer i+1 may read what layer i wrote (e.g. a whole IFBlock:
+ * conv0a, conv0b, 8 x ResConv, lastconv -- IFNet_HDv3.py:84-96).  Up to two independent images
+ * (in[k] / res[k] / out[k], same geometry, shared weights) are processed side by side.
+ * Field meaning as in drba_conv_tc_f16; act: 0 none, 1 LeakyReLU(0.2), 2 PReLU(slope[cout_pad]), 3 ReLU.
+ * sync_ws: 8 zero bytes of device memory (8-byte aligned) owned by the caller, required when
+ * nlayers > 1; zero again when the launch completes.  Do not run two programs that share a device
+ * concurrently on different streams (each expects to own all SMs between its barriers). */
+#define DRBA_CONV_MAX_LAYERS 12
+typedef struct drba_conv_layer {
+    const void* in[2];
+    const void* res[2];
+    void* out[2];
+    const void* w;
+    const float* bias;
+    const float* slope;
+    int H, W, Cin, G, T;
+    int dy[36], dx[36];
+    int cout_pad, cout, S, OH, OW, epilogue, act, out_cstride, out_os;
+} drba_conv_layer;
+DRBA_API int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nimg, void* sync_ws, void* stream);
+/* debug: while a device buffer of 4096 int64 is registered, CTA 0 of every conv launch writes clock64() stamps
+ * of its pipeline events into it (NULL switches tracing off; scripts/trace_conv.py decodes). */
+DRBA_API int drba_conv_tc_debug_trace(void* dev_buf_4096_i64);
+
 /* ---------------------------------------------------------------------------
  * Fused non-conv stages of IFNet.forward (IFNet_HDv3.py:126-177), batch 1.
  * Feature maps f0/f1: [H][W][16] (NHWC) of feat_dtype.  The only full-resolution state is

@@ -109,3 +109,44 @@ def test_rife_fp16_engine_vs_golden(golden_rife):
         p2 = _psnr(o1[2].cpu(), torch.from_numpy(g[f"{tag}_w0_1.4"]))
         print(f"[{tag}] fp16 engine PSNR vs fp32 reference: ts0.4 {p:.1f} dB, drba 0.6 {p1:.1f} dB, 1.4 {p2:.1f} dB")
         assert min(p, p1, p2) >= min_psnr, (tag, p, p1, p2)
+
+
+@pytest.mark.parametrize("c,h,w,nimg", [(32, 24, 40, 1), (64, 17, 30, 2), (192, 17, 30, 2), (16, 68, 120, 2)])
+def test_conv_program_chain_vs_torch(c, h, w, nimg):
+    """A persistent multi-layer program (stride-2 conv -> 3 x ResConv-style conv with residual, grid
+    barrier between layers, 1-2 images sharing the launch) against a layer-by-layer torch reference
+    that rounds the activations to fp16 between layers like the kernel does."""
+    from drba_b200.ifnet import _tc_conv3x3
+    eng = _engine()
+    g = torch.Generator(device="cpu").manual_seed(c + h + nimg)
+    cin0 = 32
+    w0 = torch.randn((c, cin0, 3, 3), generator=g) * (1.0 / (cin0 * 9)) ** 0.5
+    b0 = torch.randn((c,), generator=g) * 0.1
+    ws = [torch.randn((c, c, 3, 3), generator=g) * (0.5 / (c * 9)) ** 0.5 for _ in range(3)]
+    bs = [torch.randn((c,), generator=g) * 0.1 for _ in range(3)]
+    l0 = _tc_conv3x3(w0, b0, 2, 1, "cuda")
+    ls = [_tc_conv3x3(wi, bi, 1, 1, "cuda") for wi, bi in zip(ws, bs)]
+    xs = [torch.randn((1, cin0, 2 * h, 2 * w), generator=g).half() for _ in range(nimg)]
+    x_dev = [x[0].permute(1, 2, 0).contiguous().cuda() for x in xs]
+    cp = l0.cout_pad
+    p0 = [torch.zeros((h, w, cp), dtype=torch.float16, device="cuda") for _ in range(nimg)]
+    p1 = [torch.zeros((h, w, cp), dtype=torch.float16, device="cuda") for _ in range(nimg)]
+    steps = [(l0, 2 * h, 2 * w, x_dev, p0, h, w, cp, None)]
+    cur, nxt = p0, p1
+    for layer in ls:
+        steps.append((layer, h, w, cur, nxt, h, w, cp, cur))
+        cur, nxt = nxt, cur
+    for rep in range(2):       # second run checks that the barrier words were left zeroed
+        eng._conv_program(steps)
+    torch.cuda.synchronize()
+    assert int(eng._sync.abs().sum().item()) == 0
+    for k in range(nimg):
+        y = _lrelu(F.conv2d(xs[k].float(), w0.half().float(), b0, 2, 1)).half()
+        for wi, bi in zip(ws, bs):
+            y = _lrelu(F.conv2d(y.float(), wi.half().float(), bi, 1, 1) + y.float()).half()
+        ref = y[0].permute(1, 2, 0).float()
+        got = cur[k][:, :, :c].float().cpu()
+        assert torch.isfinite(got).all()
+        err = (got - ref).abs()
+        tol = 6e-3 + 4e-3 * ref.abs()      # 4 layers of fp16 re-rounding
+        assert (err <= tol).all(), f"image {k}: max err {err.max().item():.4g}"
