@@ -5,13 +5,18 @@
 // in the reference's own GPU precision (fp16 under torch.autocast, models/rife.py:26,78).
 //
 // GEMM view: M = output pixels, N = output channels, K = taps x Cin.
-//  * activations are NHWC fp16; a tile is a 128-pixel rectangle (16x8, 32x4, ...) times an N tile of
-//    <= 128 channels; its accumulator is a [128 lanes x ntile columns] fp32 block of tensor memory;
-//  * per K step ONE tiled TMA load brings the shifted [th][tw][Kc] window of the input into shared
-//    memory as a K-major, hardware-swizzled [128 x Kc] A tile -- zero padding is TMA out-of-bounds
-//    fill, so there is no im2col buffer and no halo logic; a second TMA load brings the weight tile.
-//    Stride-2 convs view the input as [H/2][2][W/2][2][C] (rank-5 tensor map) so a tap stays a dense
-//    box.  Layers with few input channels put several taps into one pipeline stage.
+//  * activations are NHWC fp16; an M tile is a 128-pixel rectangle (16x8, 32x4, ...), the N tile is
+//    <= 128 channels; the accumulator is a [128 lanes x ntile columns] fp32 block of tensor memory;
+//  * per K step ONE tiled TMA load brings the shifted input window into shared memory as K-major,
+//    hardware-swizzled [128 x Kc] A tiles -- zero padding is TMA out-of-bounds fill, so there is no
+//    im2col buffer and no halo logic.  Stride-2 convs view the input as [H/2][2][W/2][2][C] (rank-5
+//    tensor map) so a tap stays a dense box;
+//  * thin layers (Kc = 16 / 32 channels per K step) work on SUPER TILES of 4 / 2 vertically stacked
+//    M tiles so that every TMA box still carries 16 KB (measured: a TMA instruction costs its issuing
+//    thread ~130 cycles regardless of size, which is what bounds layers with 4 KB boxes);
+//  * WEIGHTS: when all weight tiles of a layer fit in 96 KB they are loaded ONCE per layer per CTA
+//    and stay resident (every IFNet layer at the fine levels; the ring then carries activations only);
+//    otherwise they stream through the ring next to the activations, issued by a second producer warp;
 //  * ConvTranspose(4,2,1) is four 2x2-tap phase convs; the lastconv epilogue writes the
 //    PixelShuffle(2)'d NHWC fp32 [4h][4w][16] directly.
 //
@@ -20,9 +25,10 @@
 // MMA or TMA time, and the coarse IFNet levels (510 ... 8160 pixels) are pure launch latency.  So:
 //  * grid = min(tiles, 148) CTAs, one per SM; each CTA walks its tiles of the current layer with a
 //    shared-memory ring that never drains between tiles;
-//  * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-5 / 6-9 = two epilogue groups that
-//    alternate tiles over a double-buffered TMEM accumulator (the epilogue of tile i overlaps the
-//    main loop of tile i+1);
+//  * warp 0 = activation (A) producer, warp 10 = weight (B) producer, warp 1 = tcgen05.mma issuer --
+//    each runs its loop warp-converged with ONE ELECTED lane issuing, which keeps TMA / MMA operands in
+//    uniform registers; warps 2-5 / 6-9 = two epilogue groups that alternate tiles over a
+//    double-buffered TMEM accumulator (the epilogue of tile i overlaps the main loop of tile i+1);
 //  * consecutive layers (a whole IFBlock: conv0a, conv0b, 8 x ResConv, lastconv) are chained inside
 //    the launch with a grid-wide barrier (release/acquire counter in global memory) instead of a
 //    kernel boundary; up to two independent images (the two interpolated frames of a DRBA window)
@@ -34,11 +40,12 @@
 
 namespace drba {
 
-constexpr int kTcThreads = 320;        // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int kTcThreads = 352;        // warp 0 A producer, warp 1 MMA, warps 2..9 epilogue, warp 10 B producer
 constexpr int kTileM = 128;
 constexpr int kStages = 6;
-constexpr int kABytesMax = 16384;      // 128 rows x 128 B
-constexpr int kStageBytes = 32768;     // A (<= 16 KB) | B (<= 16 KB)
+constexpr int kABytesMax = 16384;      // one A stage: MT x 128 rows x Kc x 2 B
+constexpr int kStageBytes = 32768;     // streaming mode: A (<= 16 KB) | B (<= 16 KB)
+constexpr int kBRegion = 98304;        // resident mode: all weight tiles of the layer, then 6 A stages
 constexpr int kMaxNTile = 128;
 constexpr int kMaxTapsTc = 9;
 constexpr int kMaxGroups = 4;
@@ -56,15 +63,16 @@ struct alignas(64) LayerDev {
     int OH, OW;
     int Kc, kchunks;        // channels per K step, Cin / Kc
     int S, T, G;
-    int tps;                // taps per pipeline stage (> 1 only when kchunks == 1)
-    int KI;                 // pipeline iterations per tile
+    int MT;                 // M tiles per super tile (stacked vertically)
+    int KI;                 // pipeline iterations per super tile = T * kchunks
+    int resident;           // 1: weights resident in smem for the whole layer
     int ntile, nsplits, cout_pad, cout;
     int swz_bytes;          // 32 / 64 / 128
-    int a_sub, b_sub;       // byte stride between the taps of one stage
+    int b_sub;              // bytes of one weight tile (padded to the swizzle period)
     int epilogue;           // 0: NHWC fp16 (+res, act); 1: lastconv pixel shuffle -> fp32 [4*OH][4*OW][16]
     int act;                // 0 none, 1 LeakyReLU(0.2), 2 PReLU(slope), 3 ReLU
     int out_cstride, os;
-    int tiles_x, mtiles, tile_w, tile_h;
+    int tiles_x, mtiles, tile_w, tile_h;   // super-tile grid; tile_w x tile_h = one 128-pixel M tile
     int total_tiles;        // nimg * G * nsplits * mtiles
     // per (group, tap): cell offset y | cell offset x << 8 | parity y << 16 | parity x << 17 (offsets biased by +64)
     int tapc[kMaxGroups][kMaxTapsTc + 3];
@@ -155,28 +163,6 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-struct TileCoord { int img, g, nsplit, oy0, ox0; };
-
-__device__ __forceinline__ TileCoord decode_tile(const LayerDev& L, int idx) {
-    TileCoord t;
-    const int m = idx % L.mtiles;
-    int r = idx / L.mtiles;
-    t.nsplit = r % L.nsplits; r /= L.nsplits;
-    t.g = r % L.G;
-    t.img = r / L.G;
-    const int ty = m / L.tiles_x, tx = m - ty * L.tiles_x;
-    t.oy0 = ty * L.tile_h;
-    t.ox0 = tx * L.tile_w;
-    return t;
-}
-
-__device__ __forceinline__ float activate(float v, int act, float slope) {
-    if (act == 1) return v > 0.0f ? v : 0.2f * v;
-    if (act == 2) return v > 0.0f ? v : slope * v;
-    if (act == 3) return v > 0.0f ? v : 0.0f;
-    return v;
-}
-
 // grid-wide barrier between two layers of a program: every CTA arrives once per layer
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
@@ -187,18 +173,17 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
     } while (v < target && ++spins < (1u << 24));   // bail out instead of hanging the GPU if a CTA is missing
 }
 
-#define TC_TRACE(slot) do { if (trace && blockIdx.x == 0) trace[(slot)] = clock64(); } while (0)
 
-constexpr int kTapTabStride = 12;
+#define TC_TRACE(slot) do { if (trace && blockIdx.x == 0) trace[(slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ Program prog)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], acc_empty[2];
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], acc_empty[2], b_full;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ __align__(16) float s_bias[kMaxGroups * 128 > 512 ? kMaxGroups * 128 : 512];
+    __shared__ __align__(16) float s_bias[512];
     __shared__ __align__(16) float s_slope[512];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -206,15 +191,37 @@ conv_tc_kernel(const __grid_constant__ Program prog)
     const int dbg = prog.dbg;
     const int nlayers = prog.nlayers;
 
-    // per-layer tables (tap geometry, bias, PReLU slopes) live in shared memory: the layer descriptors sit
-    // in kernel-parameter space and are indexed dynamically, which makes every field access a slow
-    // generic load -- the single-thread producer / MMA loops must not touch them per iteration
+    // bias / PReLU slopes of the current layer live in shared memory (the epilogue reads them per tile)
     auto stage_tables = [&](int li) {
         const LayerDev& L = prog.L[li];
         const int nb = L.G * L.cout_pad;
         for (int i = threadIdx.x; i < nb; i += kTcThreads) s_bias[i] = L.bias[i];
         if (L.act == 2)
             for (int i = threadIdx.x; i < L.cout_pad; i += kTcThreads) s_slope[i] = L.slope[i];
+    };
+    uint32_t bprod_uses = 0;         // weight producer warp: resident layers issued so far
+    // resident mode: every weight tile of the layer, once (B producer warp, warp-converged)
+    auto load_resident_weights = [&](int li) {
+        const LayerDev& L = prog.L[li];
+        if (!L.resident) return;
+        // the previous resident layer's weight loads must have landed (nobody else waits for them when this
+        // CTA had no tile in that layer) before the region and the barrier are reused
+        if (bprod_uses > 0) mbar_wait(&b_full, (bprod_uses - 1u) & 1u);
+        ++bprod_uses;
+        if (elect_one()) {
+            const int ntiles_b = L.G * L.nsplits * L.T * L.kchunks;
+            const int b_bytes = L.ntile * L.Kc * 2, b_sub = L.b_sub, Kc = L.Kc, kchunks = L.kchunks, T = L.T;
+            const int nsplits = L.nsplits, ntile = L.ntile, cout_pad = L.cout_pad;
+            mbar_expect_tx(&b_full, (uint32_t)(ntiles_b * b_bytes));
+            int i = 0;
+            for (int gn = 0; gn < L.G * nsplits; ++gn) {
+                const int g = gn / nsplits, nsplit = gn - g * nsplits;
+                for (int tap = 0; tap < T; ++tap)
+                    for (int kc = 0; kc < kchunks; ++kc, ++i)
+                        tma_load_2d(smem + (uint32_t)(i * b_sub), &L.tb, &b_full, kc * Kc, (g * T + tap) * cout_pad + nsplit * ntile);
+            }
+        }
+        __syncwarp();
     };
 
     // let the next kernel in the stream start its prologue while this one runs (PDL)
@@ -223,8 +230,9 @@ conv_tc_kernel(const __grid_constant__ Program prog)
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[0].ta[0]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[0].tb) : "memory");
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        mbar_init(&b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -237,90 +245,126 @@ conv_tc_kernel(const __grid_constant__ Program prog)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (warp == 10) load_resident_weights(0);
     // everything above overlapped the previous kernel's tail; its results are visible after this
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) TC_TRACE(4091);
 
-    uint32_t stage = 0, phase = 0;   // smem ring position (producer and MMA thread keep their own copy)
-    uint32_t tcount = 0;             // tiles this CTA has started so far (MMA thread and epilogue warps keep their own copy)
+    uint32_t stage = 0, phase = 0;   // smem ring position (both producers and the MMA warp keep their own copy)
+    uint32_t tcount = 0;             // tiles this CTA has started so far (MMA warp and epilogue warps keep their own copy)
+    uint32_t bres_phase = 0;         // MMA warp: parity of the next resident-weights barrier phase
 
     for (int li = 0; li < nlayers; ++li) {
         const LayerDev& L = prog.L[li];
         // layer constants -> registers (once per layer)
         const int total_tiles = L.total_tiles, mtiles = L.mtiles, nsplits = L.nsplits, G = L.G;
-        const int tiles_x = L.tiles_x, tile_w = L.tile_w, tile_h = L.tile_h;
-        const int KI = L.KI, tps = L.tps, T = L.T, ntile = L.ntile;
+        const int tiles_x = L.tiles_x, tile_w = L.tile_w, tile_h = L.tile_h, MT = L.MT;
+        const int KI = L.KI, T = L.T, ntile = L.ntile, kchunks = L.kchunks, Kc = L.Kc, resident = L.resident;
+        const uint32_t a_base = resident ? smem + kBRegion : smem;
+        const uint32_t a_stride = resident ? kABytesMax : kStageBytes;
 
         if (warp == 0) {
-            // ===== TMA producer: the whole warp walks the loop, one elected lane issues =====
-            const int Kc = L.Kc, kchunks = L.kchunks, cout_pad = L.cout_pad;
-            const uint32_t a_sub = L.a_sub, b_sub = L.b_sub;
-            const uint32_t tap_bytes = (uint32_t)(((dbg & 2) ? 0 : kTileM * Kc * 2) + ((dbg & 4) ? 0 : ntile * Kc * 2));
+            // ===== activation producer: the whole warp walks the loop, one elected lane issues =====
+            const uint32_t a_bytes = (dbg & 2) ? 0u : (uint32_t)(MT * kTileM * Kc * 2);
             if (li + 1 < nlayers && elect_one()) {
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].ta[0]) : "memory");
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].tb) : "memory");
             }
-            const CUtensorMap* tb = &L.tb;
             for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x) {
                 const int m = idx % mtiles;
                 int r = idx / mtiles;
-                const int nsplit = r % nsplits; r /= nsplits;
+                r /= nsplits;
                 const int g = r % G, img = r / G;
                 const int ty = m / tiles_x;
-                const int oy0 = ty * tile_h, ox0 = (m - ty * tiles_x) * tile_w;
+                const int oy0 = ty * tile_h * MT, ox0 = (m - ty * tiles_x) * tile_w;
                 const CUtensorMap* ta = &L.ta[img];
-                const int brow0 = g * T * cout_pad + nsplit * ntile;
                 int tap = 0, kc = 0;
                 for (int it = 0; it < KI; ++it) {
                     if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 0);
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    const int ntaps = tps > 1 ? min(tps, T - tap) : 1;
                     if (elect_one()) {
-                        mbar_expect_tx(&full_bar[stage], (uint32_t)ntaps * tap_bytes);
-                        const uint32_t sa = smem + stage * kStageBytes;
-                        for (int u = 0; u < ntaps; ++u) {
-                            const int e = L.tapc[g][tap + u];
-                            const int cy = (e & 0xff) - 64, cx = ((e >> 8) & 0xff) - 64, pary = (e >> 16) & 1, parx = (e >> 17) & 1;
-                            if (!(dbg & 2)) tma_load_5d(sa + u * a_sub, ta, &full_bar[stage], kc * Kc, parx, ox0 + cx, pary, oy0 + cy);
-                            if (!(dbg & 4)) tma_load_2d(sa + kABytesMax + u * b_sub, tb, &full_bar[stage], kc * Kc, brow0 + (tap + u) * cout_pad);
-                        }
+                        mbar_expect_tx(&full_bar[stage], a_bytes);
+                        if (resident) mbar_arrive(&full_bar[stage]);      // stands in for the weight producer
+                        const int e = L.tapc[g][tap];
+                        const int cy = (e & 0xff) - 64, cx = ((e >> 8) & 0xff) - 64, pary = (e >> 16) & 1, parx = (e >> 17) & 1;
+                        if (!(dbg & 2)) tma_load_5d(a_base + stage * a_stride, ta, &full_bar[stage], kc * Kc, parx, ox0 + cx, pary, oy0 + cy);
                     }
                     __syncwarp();
                     if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 1);
-                    if (tps > 1) tap += ntaps;
-                    else if (++kc == kchunks) { kc = 0; ++tap; }
+                    if (++kc == kchunks) { kc = 0; ++tap; }
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
+            }
+        } else if (warp == 10) {
+            // ===== weight producer (streaming mode only; resident weights were issued at the layer boundary) =====
+            if (!resident) {
+                const uint32_t b_bytes = (dbg & 4) ? 0u : (uint32_t)(ntile * Kc * 2);
+                const int cout_pad = L.cout_pad;
+                const CUtensorMap* tb = &L.tb;
+                for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x) {
+                    int r = idx / mtiles;
+                    const int nsplit = r % nsplits; r /= nsplits;
+                    const int g = r % G;
+                    const int brow0 = g * T * cout_pad + nsplit * ntile;
+                    int tap = 0, kc = 0;
+                    for (int it = 0; it < KI; ++it) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        if (elect_one()) {
+                            mbar_expect_tx(&full_bar[stage], b_bytes);
+                            if (!(dbg & 4)) tma_load_2d(smem + stage * kStageBytes + kABytesMax, tb, &full_bar[stage], kc * Kc, brow0 + tap * cout_pad);
+                        }
+                        __syncwarp();
+                        if (++kc == kchunks) { kc = 0; ++tap; }
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            } else {
+                // keep the ring position in step with the other warps
+                const int mine = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+                const uint32_t adv = (uint32_t)mine * (uint32_t)KI;
+                const uint32_t pos = stage + adv;
+                phase ^= (pos / kStages) & 1u;
+                stage = pos % kStages;
             }
         } else if (warp == 1) {
             // ===== MMA issuer: whole warp in the loop, one elected lane issues =====
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, K-major both,
             // N >> 3 at [17,23), M >> 4 at [24,29)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(ntile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-            const int ksteps = (dbg & 1) ? 0 : (L.Kc >> 4);
-            const uint32_t a_sub16 = (uint32_t)L.a_sub >> 4, b_sub16 = (uint32_t)L.b_sub >> 4;
+            const int ksteps = (dbg & 1) ? 0 : (Kc >> 4);
+            const uint32_t a_mt16 = (uint32_t)(kTileM * Kc * 2) >> 4;     // one M tile inside the stage
+            const uint32_t b_sub16 = (uint32_t)L.b_sub >> 4;
             const uint64_t desc_hi = make_desc(0, L.swz_bytes);
+            const uint32_t a_base16 = (a_base & 0x3FFFFu) >> 4, a_stride16 = a_stride >> 4;
+            const uint32_t b_res16 = (smem & 0x3FFFFu) >> 4;
+            if (resident && total_tiles > (int)blockIdx.x) {
+                mbar_wait(&b_full, bres_phase);
+                tc_fence_after();
+            }
+            if (resident) bres_phase ^= 1u;
             for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount) {
                 const uint32_t buf = tcount & 1u, use = tcount >> 1;
+                int r = idx / mtiles;
+                const int nsplit = r % nsplits; r /= nsplits;
+                const int g = r % G;
+                const uint32_t b_tile16 = b_res16 + (uint32_t)((g * nsplits + nsplit) * KI) * b_sub16;   // resident: tiles of (g, nsplit)
                 mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);     // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * (uint32_t)kMaxNTile;
                 uint32_t accumulate = 0;
-                int tap = 0;
                 for (int it = 0; it < KI; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 2);
-                    const int ntaps = tps > 1 ? min(tps, T - tap) : 1;
-                    tap += ntaps;
-                    const uint32_t sa16 = ((smem + stage * kStageBytes) & 0x3FFFFu) >> 4;
+                    const uint32_t sa16 = a_base16 + stage * a_stride16;
+                    const uint32_t sb16 = resident ? b_tile16 + (uint32_t)it * b_sub16 : sa16 + (kABytesMax >> 4);
                     if (elect_one()) {
-                        for (int u = 0; u < ntaps; ++u) {
-                            const uint64_t da = desc_hi | (uint64_t)(sa16 + u * a_sub16);
-                            const uint64_t db = desc_hi | (uint64_t)(sa16 + (kABytesMax >> 4) + u * b_sub16);
+                        const uint64_t db = desc_hi | (uint64_t)sb16;
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t da = desc_hi | (uint64_t)(sa16 + mt * a_mt16);
                             for (int k = 0; k < ksteps; ++k) {
                                 // advance 16 fp16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
-                                tc_mma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)(u | k));
+                                tc_mma_f16(tmem_d + mt * ntile + ((dbg & 8) ? (k & 1) * 64 : 0) + ((dbg & 16) ? (k & 3) * 32 : 0), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
                             }
                         }
                         tc_commit(&empty_bar[stage]);
@@ -350,110 +394,116 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 const int nsplit = r % nsplits; r /= nsplits;
                 const int g = r % G, img = r / G;
                 const int ty = m / tiles_x;
-                const int oy = ty * tile_h + ry, ox = (m - ty * tiles_x) * tile_w + rx;
-                const bool valid = oy < OH && ox < OW;
+                const int oy_s = ty * tile_h * MT + ry, ox = (m - ty * tiles_x) * tile_w + rx;
                 const int nbase = nsplit * ntile;
                 const float* bias = s_bias + g * cout_pad + nbase;
-                const uint32_t taddr = tmem_base + buf * (uint32_t)kMaxNTile + ((uint32_t)(q * 32) << 16);
-                if (epilogue == 0) {
-                    const size_t pix = os == 1 ? (size_t)oy * OW + ox
-                                               : (size_t)(oy * os + (g >> 1)) * (OW * os) + (ox * os + (g & 1));
-                    __half* out = reinterpret_cast<__half*>(L.out[img]) + pix * cstride + nbase;
-                    const __half* resb = L.res[img];
-                    const __half* res = (resb && valid) ? resb + pix * cstride + nbase : nullptr;
-                    // the residual does not depend on the accumulator: fetch (up to) 64 channels before waiting
-                    uint4 rpre[8];
-                    if (res) {
+                const uint32_t taddr0 = tmem_base + buf * (uint32_t)kMaxNTile + ((uint32_t)(q * 32) << 16);
+                const __half* resb = (epilogue == 0) ? L.res[img] : nullptr;
+                // the residual does not depend on the accumulator: fetch (up to) 64 channels of the first M tile before waiting
+                uint4 rpre[8];
+                {
+                    const bool v0 = oy_s < OH && ox < OW;
+                    if (resb && v0) {
+                        const __half* res = resb + ((size_t)oy_s * OW + ox) * cstride + nbase;
 #pragma unroll
                         for (int h = 0; h < 8; ++h)
                             if (h * 8 < ntile) rpre[h] = reinterpret_cast<const uint4*>(res)[h];
                     }
-                    mbar_wait(&acc_full[buf], use & 1u);
-                    tc_fence_after();
-                    if (idx == blockIdx.x && q == 2 && lane == 0) TC_TRACE(li * 256 + 200);
-                    for (int c0 = 0; c0 < ntile; c0 += 32) {
-                        uint32_t rr[32];
-                        tc_ld16_nowait(taddr + c0, rr);
-                        if (c0 + 16 < ntile) tc_ld16_nowait(taddr + c0 + 16, rr + 16);
-                        tc_ld_wait();
-                        if (!valid) continue;
+                }
+                mbar_wait(&acc_full[buf], use & 1u);
+                tc_fence_after();
+                if (idx == blockIdx.x && q == 2 && lane == 0) TC_TRACE(li * 256 + 200);
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int oy = oy_s + mt * tile_h;
+                    const bool valid = oy < OH && ox < OW;
+                    const uint32_t taddr = taddr0 + (uint32_t)(mt * ntile);
+                    if (epilogue == 0) {
+                        const size_t pix = os == 1 ? (size_t)oy * OW + ox
+                                                   : (size_t)(oy * os + (g >> 1)) * (OW * os) + (ox * os + (g & 1));
+                        __half* out = reinterpret_cast<__half*>(L.out[img]) + pix * cstride + nbase;
+                        const __half* res = (resb && valid) ? resb + pix * cstride + nbase : nullptr;
+                        for (int c0 = 0; c0 < ntile; c0 += 32) {
+                            uint32_t rr[32];
+                            tc_ld16_nowait(taddr + c0, rr);
+                            if (c0 + 16 < ntile) tc_ld16_nowait(taddr + c0 + 16, rr + 16);
+                            tc_ld_wait();
+                            if (!valid) continue;
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const int c = c0 + hh * 16;
-                            if (c >= ntile || nbase + c >= cout) continue;
-                            float v[16];
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int c = c0 + hh * 16;
+                                if (c >= ntile || nbase + c >= cout) continue;
+                                float v[16];
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(bias + c + i);
-                                v[i] = __uint_as_float(rr[hh * 16 + i]) + b4.x;
-                                v[i + 1] = __uint_as_float(rr[hh * 16 + i + 1]) + b4.y;
-                                v[i + 2] = __uint_as_float(rr[hh * 16 + i + 2]) + b4.z;
-                                v[i + 3] = __uint_as_float(rr[hh * 16 + i + 3]) + b4.w;
-                            }
-                            if (res) {
+                                for (int i = 0; i < 16; i += 4) {
+                                    const float4 b4 = *reinterpret_cast<const float4*>(bias + c + i);
+                                    v[i] = __uint_as_float(rr[hh * 16 + i]) + b4.x;
+                                    v[i + 1] = __uint_as_float(rr[hh * 16 + i + 1]) + b4.y;
+                                    v[i + 2] = __uint_as_float(rr[hh * 16 + i + 2]) + b4.z;
+                                    v[i + 3] = __uint_as_float(rr[hh * 16 + i + 3]) + b4.w;
+                                }
+                                if (res) {
 #pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    uint4 rv;
-                                    if (c0 == 0) rv = rpre[hh * 2 + h];
-                                    else if (c0 == 32) rv = rpre[4 + hh * 2 + h];
-                                    else rv = reinterpret_cast<const uint4*>(res + c)[h];
-                                    const __half2* hp = reinterpret_cast<const __half2*>(&rv);
+                                    for (int h = 0; h < 2; ++h) {
+                                        uint4 rv;
+                                        if (mt == 0 && c0 == 0) rv = rpre[hh * 2 + h];
+                                        else if (mt == 0 && c0 == 32) rv = rpre[4 + hh * 2 + h];
+                                        else rv = reinterpret_cast<const uint4*>(res + c)[h];
+                                        const __half2* hp = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        const float2 f = __half22float2(hp[k]);
-                                        v[h * 8 + k * 2] += f.x; v[h * 8 + k * 2 + 1] += f.y;
+                                        for (int k = 0; k < 4; ++k) {
+                                            const float2 f = __half22float2(hp[k]);
+                                            v[h * 8 + k * 2] += f.x; v[h * 8 + k * 2 + 1] += f.y;
+                                        }
                                     }
                                 }
+                                if (act == 1) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.0f ? v[i] : 0.2f * v[i];
+                                } else if (act == 2) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.0f ? v[i] : s_slope[nbase + c + i] * v[i];
+                                } else if (act == 3) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+                                }
+                                uint4 o[2];
+                                __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) oh[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                                uint4* o4 = reinterpret_cast<uint4*>(out + c);
+                                o4[0] = o[0]; o4[1] = o[1];
                             }
-                            if (act == 1) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.0f ? v[i] : 0.2f * v[i];
-                            } else if (act == 2) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.0f ? v[i] : s_slope[nbase + c + i] * v[i];
-                            } else if (act == 3) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-                            }
-                            uint4 o[2];
-                            __half2* oh = reinterpret_cast<__half2*>(o);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) oh[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-                            uint4* o4 = reinterpret_cast<uint4*>(out + c);
-                            o4[0] = o[0]; o4[1] = o[1];
                         }
-                    }
-                } else {
-                    // lastconv: group g = phase (py, px); channel co = c13*4 + i*2 + j lands at
-                    // out[4*oy + 2*py + i][4*ox + 2*px + j][c13]  (ConvTranspose phase + PixelShuffle(2))
-                    const int py = g >> 1, px = g & 1;
-                    const int OW4 = OW * 4;
-                    float* out = reinterpret_cast<float*>(L.out[img]);
-                    mbar_wait(&acc_full[buf], use & 1u);
-                    tc_fence_after();
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
-                        uint32_t rr[32];
-                        tc_ld16_nowait(taddr + c0, rr);
-                        tc_ld16_nowait(taddr + c0 + 16, rr + 16);
-                        tc_ld_wait();
-                        if (!valid) continue;
+                    } else {
+                        // lastconv: group g = phase (py, px); channel co = c13*4 + i*2 + j lands at
+                        // out[4*oy + 2*py + i][4*ox + 2*px + j][c13]  (ConvTranspose phase + PixelShuffle(2))
+                        const int py = g >> 1, px = g & 1;
+                        const int OW4 = OW * 4;
+                        float* out = reinterpret_cast<float*>(L.out[img]);
+                        for (int c0 = 0; c0 < 64; c0 += 32) {
+                            uint32_t rr[32];
+                            tc_ld16_nowait(taddr + c0, rr);
+                            tc_ld16_nowait(taddr + c0 + 16, rr + 16);
+                            tc_ld_wait();
+                            if (!valid) continue;
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const int c = c0 + hh * 16;
-                            float v[16];
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int c = c0 + hh * 16;
+                                float v[16];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[hh * 16 + i]) + bias[c + i];
+                                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[hh * 16 + i]) + bias[c + i];
 #pragma unroll
-                            for (int ij = 0; ij < 4; ++ij) {
-                                const int yy = 4 * oy + 2 * py + (ij >> 1), xx = 4 * ox + 2 * px + (ij & 1);
-                                const float4 o = make_float4(v[0 + ij], v[4 + ij], v[8 + ij], v[12 + ij]);
-                                *reinterpret_cast<float4*>(out + ((size_t)yy * OW4 + xx) * 16 + (c >> 2)) = o;
+                                for (int ij = 0; ij < 4; ++ij) {
+                                    const int yy = 4 * oy + 2 * py + (ij >> 1), xx = 4 * ox + 2 * px + (ij & 1);
+                                    const float4 o = make_float4(v[0 + ij], v[4 + ij], v[8 + ij], v[12 + ij]);
+                                    *reinterpret_cast<float4*>(out + ((size_t)yy * OW4 + xx) * 16 + (c >> 2)) = o;
+                                }
                             }
                         }
                     }
                 }
                 if (idx == blockIdx.x && q == 2 && lane == 0) TC_TRACE(li * 256 + 201);
-                // accumulator drained: hand the buffer back to the MMA thread
+                // accumulator drained: hand the buffer back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -466,6 +516,9 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             __threadfence();
             asm volatile("fence.proxy.async;" ::: "memory");
             __syncthreads();
+            // this CTA's MMAs are done: the next layer's resident weights may overwrite the weight region while
+            // the grid barrier is pending (weights do not depend on other CTAs)
+            if (warp == 10) load_resident_weights(li + 1);
             if (threadIdx.x == 0) { TC_TRACE(li * 256 + 202); grid_barrier(prog.sync, (unsigned)(li + 1) * gridDim.x); TC_TRACE(li * 256 + 203); }
             stage_tables(li + 1);
             __syncthreads();
@@ -490,7 +543,6 @@ conv_tc_kernel(const __grid_constant__ Program prog)
         }
     }
 }
-
 
 // ---- host side ---------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -530,6 +582,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     if (d.epilogue == 0 && ((d.out_os == 1 && G != 1) || (d.out_os == 2 && G != 4))) return DRBA_E_ARG;
     if (d.epilogue == 0 && (d.out_cstride < d.cout_pad || d.out_cstride % 8 != 0)) return DRBA_E_ARG;
     if (d.act < 0 || d.act > 3 || (d.act == 2 && !d.slope)) return DRBA_E_ARG;
+    if (d.out_os != 1 && (d.res[0] || d.res[1])) return DRBA_E_ARG;   // residuals only for same-geometry layers
     if (G * d.cout_pad > 512) return DRBA_E_UNSUPPORTED;   // bias / slope tables staged in shared memory
     if (!aligned16(d.w)) return DRBA_E_ALIGN;
     for (int i = 0; i < nimg; ++i) {
@@ -551,22 +604,36 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
             if (S == 2) { pary = dy & 1; parx = dx & 1; cy = (dy - pary) >> 1; cx = (dx - parx) >> 1; }
             L.tapc[gi][t] = (cy + 64) | ((cx + 64) << 8) | (pary << 16) | (parx << 17);
         }
-    // pixel patch of a tile: the 128-pixel rectangle that covers the output with the fewest tiles
-    int best_tiles = 1 << 30;
-    L.tile_w = 16; L.tile_h = 8;
-    const int shapes[5][2] = {{16, 8}, {32, 4}, {8, 16}, {64, 2}, {128, 1}};
-    for (int i = 0; i < 5; ++i) {
-        const int nt = ((OW + shapes[i][0] - 1) / shapes[i][0]) * ((OH + shapes[i][1] - 1) / shapes[i][1]);
-        if (nt < best_tiles) { best_tiles = nt; L.tile_w = shapes[i][0]; L.tile_h = shapes[i][1]; }
-    }
-    L.tiles_x = (OW + L.tile_w - 1) / L.tile_w;
-    L.mtiles = L.tiles_x * ((OH + L.tile_h - 1) / L.tile_h);
-    // N tile: <= 128 columns, a multiple of 16 that divides cout_pad; small layers are split further
-    // so that more SMs stream the K loop in parallel
+    // N tile: <= 128 columns, a multiple of 16 that divides cout_pad
     int ntile = 0;
     for (int cand = d.cout_pad < kMaxNTile ? d.cout_pad : kMaxNTile; cand >= 16; cand -= 16)
         if (d.cout_pad % cand == 0) { ntile = cand; break; }
     if (!ntile) return DRBA_E_UNSUPPORTED;
+    // M tiles per super tile: thin K steps stack M tiles so that one TMA box still carries 16 KB
+    int MT = kABytesMax / (kTileM * L.Kc * 2);
+    while (MT > 1 && MT * ntile > kMaxNTile) MT >>= 1;
+    // pixel patch of an M tile: the rectangle whose super tiles cover the output with the least waste
+    long best = -1;
+    const int shapes[5][2] = {{16, 8}, {32, 4}, {8, 16}, {64, 2}, {128, 1}};
+    int best_mt = 1;
+    L.tile_w = 16; L.tile_h = 8;
+    for (int mt = MT; mt >= 1; mt >>= 1) {
+        for (int i = 0; i < 5; ++i) {
+            const int sh = shapes[i][1] * mt;
+            if (sh > 256) continue;
+            const long nt = (long)((OW + shapes[i][0] - 1) / shapes[i][0]) * ((OH + sh - 1) / sh);
+            const long cost = nt * mt;       // covered M tiles (waste included)
+            // prefer the larger super tile unless it wastes > 6 % more coverage
+            if (best < 0 || cost * 100 < best * 94 || (mt == best_mt && cost < best)) {
+                best = cost; best_mt = mt; L.tile_w = shapes[i][0]; L.tile_h = shapes[i][1];
+            }
+        }
+    }
+    MT = best_mt;
+    L.MT = MT;
+    L.tiles_x = (OW + L.tile_w - 1) / L.tile_w;
+    L.mtiles = L.tiles_x * ((OH + L.tile_h * MT - 1) / (L.tile_h * MT));
+    // small layers: split N further so that more SMs stream the K loop in parallel
     if (d.epilogue == 0) {
         while (ntile >= 64 && ntile % 32 == 0 && nimg * L.mtiles * G * (d.cout_pad / ntile) * 2 <= kNumSMs) ntile /= 2;
     }
@@ -576,31 +643,25 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     L.out_cstride = d.out_cstride; L.os = d.out_os;
     for (int i = 0; i < nimg; ++i) { L.res[i] = (const __half*)d.res[i]; L.out[i] = d.out[i]; }
 
-    // taps per stage: thin layers (one K chunk per tap) put several taps behind one barrier so that a
-    // stage carries ~16 KB of activations
-    const int a_bytes = kTileM * L.Kc * 2, b_bytes = ntile * L.Kc * 2;
+    const int b_bytes = ntile * L.Kc * 2;
     const int swz_period = 8 * L.swz_bytes;
-    L.a_sub = a_bytes;                                            // 4096 / 8192 / 16384: multiples of every period
     L.b_sub = (b_bytes + swz_period - 1) / swz_period * swz_period;
-    L.tps = 1;
-    if (L.kchunks == 1) {
-        int tps = kABytesMax / a_bytes;
-        while (tps > 1 && tps * L.b_sub > kStageBytes - kABytesMax) --tps;
-        if (tps > T) tps = T;
-        // balance: e.g. 9 taps with room for 4 -> 3 stages of 3
-        const int iters = (T + tps - 1) / tps;
-        tps = (T + iters - 1) / iters;
-        L.tps = tps;
+    L.KI = T * L.kchunks;
+    // weights resident in shared memory when every tile of the layer fits
+    L.resident = ((long)G * L.nsplits * L.KI * L.b_sub <= (long)kBRegion) ? 1 : 0;
+    {
+        static int env_res = -1;
+        if (env_res < 0) { const char* e = getenv("DRBA_TC_RESIDENT"); env_res = e ? atoi(e) : 1; }
+        if (!env_res) L.resident = 0;
     }
-    L.KI = L.tps > 1 ? (T + L.tps - 1) / L.tps : T * L.kchunks;
-    if (L.b_sub * L.tps > kStageBytes - kABytesMax) return DRBA_E_UNSUPPORTED;
+    if (L.b_sub > kStageBytes - kABytesMax) return DRBA_E_UNSUPPORTED;
 
     // A: input viewed as [H/S][S][W/S][S][C], innermost first
     for (int i = 0; i < nimg; ++i) {
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)S, (cuuint64_t)(W / S), (cuuint64_t)S, (cuuint64_t)(H / S)};
         const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)S * Cin * 2, (cuuint64_t)W * Cin * 2,
                                        (cuuint64_t)S * W * Cin * 2};
-        const cuuint32_t box[5] = {(cuuint32_t)L.Kc, 1, (cuuint32_t)L.tile_w, 1, (cuuint32_t)L.tile_h};
+        const cuuint32_t box[5] = {(cuuint32_t)L.Kc, 1, (cuuint32_t)L.tile_w, 1, (cuuint32_t)(L.tile_h * L.MT)};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         const CUresult r = encode(&L.ta[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d.in[i]), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(L.swz_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -659,7 +720,7 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
     int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
     if (env_grid > 0 && env_grid < grid) grid = env_grid;
     static bool attr_set = false;
-    const size_t smem = (size_t)kStages * kStageBytes + 1024;
+    const size_t smem = (size_t)kBRegion + (size_t)kStages * kABytesMax + 1024;   // == kStages * kStageBytes + 1024
     if (!attr_set) {
         cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;

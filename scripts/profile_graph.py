@@ -67,6 +67,16 @@ def main():
     print(json.dumps({k: out[k] for k in ("sum_kernel_us_per_window", "span_us_per_window")}))
     for k, v in out["kernels"].items():
         print(f"{v['share']:7.3f} {v['per_window']:7.1f} {v['avg_us']:9.2f} us  {k}")
+    # every kernel of two consecutive windows in start order
+    seq = [(e.time_range.start, e.name.split("(")[0].replace("void ", "").replace("drba::", "")[:48],
+            e.device_time if hasattr(e, "device_time") else e.cuda_time) for e in prof.events()
+           if e.device_type == torch.autograd.DeviceType.CUDA]
+    seq.sort()
+    nper = len(seq) // args.windows if args.windows else 0
+    with open(args.out.replace(".json", "_seq.txt"), "w") as f:
+        t00 = seq[0][0] if seq else 0
+        for st, name, dur in seq[:2 * nper]:
+            f.write(f"{(st - t00):10.1f} {dur:9.2f}  {name}\n")
     # per-launch list of the conv kernel in graph order (one window), to map layers
     conv = [(e.time_range.start, e.device_time if hasattr(e, "device_time") else e.cuda_time) for e in prof.events()
             if e.device_type == torch.autograd.DeviceType.CUDA and "conv_tc" in e.name]
