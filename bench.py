@@ -10,9 +10,9 @@ A "step" is one sliding-triplet window of the reference's driver loop (infer.py:
 interpolated).  The metric is OUTPUT frames per second at net-input size 1088x1920.
 
 * value : whole-job frames/s with the frames already resident in HBM (CUDA events, K steps).
-* e2e   : the same through the public API with HOST buffers: every step copies the new frame
-          from pinned host memory to the device and every output frame back (fp32, like the
-          reference's to_inp / to_out, models/utils/tools.py:59-68).
+* e2e   : the same through the public API with HOST buffers: every step uploads the window's new
+          decoded uint8 frame from pinned host memory (to_inp) and downloads every output frame as
+          uint8 (to_out, models/utils/tools.py:59-68), on copy streams next to the compute stream.
 * roofline : the dominant kernel family of the step, timed live with CUDA events in an
           instrumented pass of the same steps (drba_b200._lib.LaunchProfiler).
 * cpu_baseline : the oracle port of the reference path (oracle/ifnet.py, torch fp32 CPU convs +
@@ -202,8 +202,6 @@ def main():
     K, Wm = args.steps, args.warmup
     ring = 8
     frames = synth_clip(ring, h, w, 1000 + rank, dev)     # each rank: its own shard of the stream
-    host_frames = [f.cpu().pin_memory() for f in frames]
-    frame_bytes = frames[0].numel() * 4
 
     def window(j, reuse, src):
         return model.inference_ts_drba(src[j % ring], src[(j + 1) % ring], src[(j + 2) % ring], TS_PATTERN[j % 2], reuse, True)
@@ -245,40 +243,46 @@ def main():
     step_ms = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(K))
     launches = _lib.KERNEL_LAUNCHES - launches0
 
-    # ---- end to end through the public API with host buffers -----------------------------------
-    out_host = [torch.empty((1, 3, h, w), dtype=torch.float32).pin_memory() for _ in range(3)]
-    dev_in = [torch.empty_like(frames[0]) for _ in range(3)]
-    for k in range(3):
-        dev_in[k].copy_(host_frames[k], non_blocking=True)
+    # ---- end to end through the public API with HOST buffers ------------------------------------------
+    # host side = what the reference's driver loop holds (infer.py:112-156): decoded uint8 BGR frames
+    # [1080,1920,3] in, encoded-ready uint8 frames out.  Every step uploads the window's new frame
+    # (to_inp: H2D + /255 + resize to the 1088x1920 net input, one fused kernel) and downloads EVERY output
+    # frame (to_out: resize back + *255 + uint8 + D2H); copies ride two copy streams (drba_b200.tools.FrameIO).
+    from drba_b200.tools import FrameIO
+    io = FrameIO((H_SRC, W_SRC), (h, w), dev)
+    host_u8 = []
+    for f in frames:
+        f8 = torch.nn.functional.interpolate(f, size=(H_SRC, W_SRC), mode="bilinear", align_corners=False)
+        host_u8.append((f8[0].permute(1, 2, 0) * 255.0).clamp(0, 255).to(torch.uint8).contiguous().cpu().pin_memory())
+    win = [io.upload(host_u8[0]), io.upload(host_u8[1])]
     reuse_e = None
-    h2d = d2h = 0
 
-    def e2e_window(j, reuse_e, count):
-        nonlocal h2d, d2h
-        # the new frame of this window arrives from the host (to_inp); I0/I1 are carried over
-        slot = (j + 2) % 3
-        dev_in[slot].copy_(host_frames[(j + 2) % ring], non_blocking=True)
-        I0, I1, I2 = dev_in[j % 3], dev_in[(j + 1) % 3], dev_in[slot]
+    def e2e_window(j, reuse_e):
+        win.append(io.upload(host_u8[(j + 2) % ring]))     # the new frame of this window arrives from the host
+        I0, I1, I2 = win[-3], win[-2], win[-1]
         out, reuse_e = model.inference_ts_drba(I0, I1, I2, TS_PATTERN[j % 2], reuse_e, True)
-        for k, o in enumerate(out):
-            out_host[k].copy_(o, non_blocking=True)          # to_out: every output frame goes back
-        if count:
-            h2d += frame_bytes
-            d2h += frame_bytes * len(out)
+        io.release_inputs()
+        for o in out:
+            io.download(o)                                  # every output frame goes back to the host
+        del win[0]
         return len(out), reuse_e
 
     for j in range(Wm):
-        _, reuse_e = e2e_window(j, reuse_e, False)
+        _, reuse_e = e2e_window(j, reuse_e)
+    io.drain()
     barrier()
+    io.h2d_bytes = io.d2h_bytes = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nout_e = 0
     e0.record()
     for j in range(Wm, Wm + K):
-        n, reuse_e = e2e_window(j, reuse_e, True)
+        n, reuse_e = e2e_window(j, reuse_e)
         nout_e += n
+    io.drain()
     e1.record()
     barrier()
     ms_e = e0.elapsed_time(e1)
+    h2d, d2h = io.h2d_bytes, io.d2h_bytes
     clk = clocks.stop()
 
     # ---- instrumented pass: per-kernel-family shares and the roofline ------------------------------

@@ -34,6 +34,8 @@ SIGNATURES = {
     "drba_drm_gmfss_f32": (_I, [_D, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "drba_backwarp_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "drba_resize_bilinear_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
+    "drba_frame_ingest_u8": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "drba_frame_egress_u8": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "drba_conv2d_direct_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P,
                                     _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "drba_conv_tc_f16": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),

@@ -77,6 +77,66 @@ resize_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, in
     }
 }
 
+
+// ---- frame ingest / egress (models/utils/tools.py:33-38, :59-72) -----------------------------------
+// to_inp:  uint8 HWC (BGR as decoded) -> float NCHW / 255 -> F.interpolate(size, bilinear, align_corners=False)
+// to_out:  F.interpolate(src_size) -> * 255. -> astype(uint8) (C cast: truncation, wraps outside [0, 256))
+// One pass each: the fp32 full-size intermediate of the reference never exists, and the host<->device
+// copies carry 1 byte per sample instead of 4.
+__global__ void __launch_bounds__(kSampleThreads)
+frame_ingest_u8_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, int H, int W, int OH, int OW,
+                       float rh, float rw)
+{
+    const size_t OHW = (size_t)OH * OW;
+    const size_t p = (size_t)blockIdx.x * kSampleThreads + threadIdx.x;
+    if (p >= OHW) return;
+    const int oy = (int)(p / OW), ox = (int)(p - (size_t)oy * OW);
+    float sy = rh * ((float)oy + 0.5f) - 0.5f, sx = rw * ((float)ox + 0.5f) - 0.5f;
+    if (sy < 0.0f) sy = 0.0f;
+    if (sx < 0.0f) sx = 0.0f;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, hy = 1.0f - ly;
+    const float lx = sx - (float)x0, hx = 1.0f - lx;
+    const unsigned char* r0 = in + ((size_t)y0 * W) * 3;
+    const unsigned char* r1 = in + ((size_t)y1 * W) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float a = (float)r0[x0 * 3 + c] / 255.0f, b = (float)r0[x1 * 3 + c] / 255.0f;
+        const float cc = (float)r1[x0 * 3 + c] / 255.0f, d = (float)r1[x1 * 3 + c] / 255.0f;
+        out[(size_t)c * OHW + p] = hy * (hx * a + lx * b) + ly * (hx * cc + lx * d);
+    }
+}
+
+__global__ void __launch_bounds__(kSampleThreads)
+frame_egress_u8_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, int H, int W, int OH, int OW,
+                       float rh, float rw)
+{
+    const size_t OHW = (size_t)OH * OW;
+    const size_t p = (size_t)blockIdx.x * kSampleThreads + threadIdx.x;
+    if (p >= OHW) return;
+    const int oy = (int)(p / OW), ox = (int)(p - (size_t)oy * OW);
+    float sy = rh * ((float)oy + 0.5f) - 0.5f, sx = rw * ((float)ox + 0.5f) - 0.5f;
+    if (sy < 0.0f) sy = 0.0f;
+    if (sx < 0.0f) sx = 0.0f;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, hy = 1.0f - ly;
+    const float lx = sx - (float)x0, hx = 1.0f - lx;
+    const size_t i00 = (size_t)y0 * W + x0, i01 = (size_t)y0 * W + x1;
+    const size_t i10 = (size_t)y1 * W + x0, i11 = (size_t)y1 * W + x1;
+    const size_t HW = (size_t)H * W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* s = in + (size_t)c * HW;
+        const float v = (hy * (hx * s[i00] + lx * s[i01]) + ly * (hx * s[i10] + lx * s[i11])) * 255.0f;
+        // numpy float32 -> uint8: truncate toward zero, keep the low 8 bits
+        const float t = truncf(v);
+        const int iv = (t >= -2147483648.0f && t < 2147483648.0f) ? (int)t : 0;
+        out[p * 3 + c] = (unsigned char)(iv & 0xff);
+    }
+}
+
 }  // namespace drba
 
 using namespace drba;
@@ -110,6 +170,24 @@ int drba_resize_bilinear_f32(const float* in, float* out, int N, int C, int H, i
     dim3 grid(cdiv((size_t)OH * OW, kSampleThreads), NC < 64 ? NC : 64);
     resize_bilinear_kernel<<<grid, kSampleThreads, 0, as_stream(stream)>>>(in, out, NC, H, W, OH, OW,
                                                                            align_corners ? 1 : 0, rh, rw);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+int drba_frame_ingest_u8(const unsigned char* in_hwc, float* out_chw, int H, int W, int OH, int OW, void* stream)
+{
+    if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || !in_hwc || !out_chw) return DRBA_E_ARG;
+    frame_ingest_u8_kernel<<<cdiv((size_t)OH * OW, kSampleThreads), kSampleThreads, 0, as_stream(stream)>>>(
+        in_hwc, out_chw, H, W, OH, OW, (float)H / (float)OH, (float)W / (float)OW);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+int drba_frame_egress_u8(const float* in_chw, unsigned char* out_hwc, int H, int W, int OH, int OW, void* stream)
+{
+    if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || !in_chw || !out_hwc) return DRBA_E_ARG;
+    frame_egress_u8_kernel<<<cdiv((size_t)OH * OW, kSampleThreads), kSampleThreads, 0, as_stream(stream)>>>(
+        in_chw, out_hwc, H, W, OH, OW, (float)H / (float)OH, (float)W / (float)OW);
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
 }

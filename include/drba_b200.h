@@ -124,6 +124,16 @@ DRBA_API int drba_resize_bilinear_f32(const float* in, float* out, int N, int C,
                                       int OH, int OW, int align_corners, float rh, float rw, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Frame ingest / egress: models/utils/tools.py:33-38 (to_tensor / to_cv2) fused with :59-72
+ * (to_inp / to_out / resize).  in_hwc / out_hwc: uint8 [H][W][3] as cv2 decodes / encodes (BGR);
+ * float side: NCHW [3][H'][W'] in [0,1].  Bilinear, align_corners=False, ATen's scale = in/out.
+ *   ingest: out = interpolate(float(in) / 255, (OH, OW))
+ *   egress: out = astype(uint8)(interpolate(in, (OH, OW)) * 255.)   (truncation; wraps like numpy)
+ * ------------------------------------------------------------------------- */
+DRBA_API int drba_frame_ingest_u8(const unsigned char* in_hwc, float* out_chw, int H, int W, int OH, int OW, void* stream);
+DRBA_API int drba_frame_egress_u8(const float* in_chw, unsigned char* out_hwc, int H, int W, int OH, int OW, void* stream);
+
+/* ---------------------------------------------------------------------------
  * fp32 direct convolution (exact engine).  Generic form covering every conv on the
  * IFNet path (models/rife_426_heavy/IFNet_HDv3.py:11-25 conv, :28-47 Head, :50-59 ResConv,
  * :80 lastconv ConvTranspose2d(4,2,1) as four phase launches):
