@@ -221,6 +221,16 @@ invert_flow_resolve_kernel(float* __restrict__ acc, float* __restrict__ out, int
     out[((size_t)n * 2 + 1) * HW + r] = oy * 2.0f;
 }
 
+
+
+// csrc/splat_gather.cu
+size_t splat_gather_workspace_bytes(int N, int H, int W);
+int splat_gather_launch(const float* in, const float* flow, const float* metric, float* out,
+                        int N, int C, int H, int W, int mode, int eps_mode, void* ws, cudaStream_t st);
+// the list-building cost of the gather path is independent of C: it wins once the scatter path would
+// need three or more 4-channel accumulator groups
+constexpr int kGatherMinChannels = 9;
+
 }  // namespace drba
 
 using namespace drba;
@@ -234,7 +244,9 @@ size_t drba_softsplat_workspace_bytes(int N, int C, int H, int W, int mode)
     const size_t groups_total = ((size_t)C + (mode != DRBA_SPLAT_SUM ? 1 : 0) + 3) / 4;
     size_t groups_cap = kSplatL2Budget / group_bytes;
     if (groups_cap < 1) groups_cap = 1;
-    return group_bytes * (groups_total < groups_cap ? groups_total : groups_cap);
+    const size_t scatter = group_bytes * (groups_total < groups_cap ? groups_total : groups_cap);
+    const size_t gather = C + (mode != DRBA_SPLAT_SUM ? 1 : 0) >= kGatherMinChannels ? splat_gather_workspace_bytes(N, H, W) : 0;
+    return scatter > gather ? scatter : gather;
 }
 
 int drba_softsplat_f32_variant(const float* in, const float* flow, const float* metric, float* out,
@@ -244,7 +256,7 @@ int drba_softsplat_f32_variant(const float* in, const float* flow, const float* 
     if (N < 0 || C < 0 || H < 0 || W < 0) return DRBA_E_ARG;
     if (mode < DRBA_SPLAT_SUM || mode > DRBA_SPLAT_SOFT) return DRBA_E_ARG;
     if (eps_mode < DRBA_EPS_ADD || eps_mode > DRBA_EPS_CLIP) return DRBA_E_ARG;
-    if (variant != 0 && variant != 1) return DRBA_E_ARG;
+    if (variant < 0 || variant > 3) return DRBA_E_ARG;
     if ((size_t)N * C * H * W == 0) return DRBA_OK;
     if (!in || !flow || !out) return DRBA_E_ARG;
     if ((mode == DRBA_SPLAT_LINEAR || mode == DRBA_SPLAT_SOFT) && !metric) return DRBA_E_ARG;
@@ -252,6 +264,19 @@ int drba_softsplat_f32_variant(const float* in, const float* flow, const float* 
     if (!ws || ws_bytes < group_bytes) return DRBA_E_WORKSPACE;
     if (!aligned16(ws)) return DRBA_E_ALIGN;
     const int has_w = mode != DRBA_SPLAT_SUM ? 1 : 0;
+    // variant: 0 = automatic, 1 = scalar atomics (the reference kernel's scheme), 2 = vector-red scatter,
+    //          3 = owner-computes gather (csrc/splat_gather.cu)
+    if (variant == 3 || (variant == 0 && C + has_w >= kGatherMinChannels)) {
+        const size_t need = splat_gather_workspace_bytes(N, H, W);
+        if (ws_bytes >= need) {
+            const int rc = splat_gather_launch(in, flow, metric, out, N, C, H, W, mode, eps_mode, ws, as_stream(stream));
+            if (rc != DRBA_E_UNSUPPORTED) return rc;
+        } else if (variant == 3) {
+            return DRBA_E_WORKSPACE;
+        }
+    }
+    if (variant == 2) variant = 0;
+    if (variant == 3) variant = 0;
     const size_t groups_fit = ws_bytes / group_bytes;
     const int cc_max = (int)(groups_fit * 4 > (size_t)(C + has_w) ? (size_t)C : groups_fit * 4 - has_w);
     cudaStream_t st = as_stream(stream);

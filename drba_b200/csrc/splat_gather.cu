@@ -1,0 +1,389 @@
+// Forward (summation) splat, OWNER-COMPUTES path for many-channel inputs (sm_100a).
+//
+// Same operator as csrc/splat.cu (models/softsplat/softsplat.py:248-293 + kernel :306-357,
+// arithmetic per SURVEY.md appendix A.1), different algorithm.  The scatter formulation needs
+// 4 x (C + 1) float atomics per source pixel; measured on B200 the L2 atomic units cap it at
+// ~0.9 TB/s of payload, i.e. 10-13 % of the HBM roofline for the 64..192-channel feature splats
+// of GMFSS.  The splat is a sparse matrix (<= 4 non-zeros per source pixel) applied to C
+// columns, so here the matrix is built once per (flow, metric) -- cost independent of C -- and
+// applied as a gather with NO float atomics:
+//
+//   1. count   : every source pixel bumps an int32 counter of each in-bounds target corner
+//   2. scan    : exclusive prefix sum of the counters -> {offset, count} per target pixel
+//   3. fill    : every source pixel writes (corner << 29 | source index) into a slot of each target's
+//                list (slot = atomicSub on the counter, which thereby returns to zero)
+//   4. gather  : one thread per TARGET pixel reads its list, sorts it by (corner, source index), recomputes
+//                the bilinear corner weights from the flow, and accumulates all C channels in registers
+//                in that order -- exactly the summation order of the reference's CPU path (corner-major:
+//                softsplat_torch.py:146-174 adds all NW contributions in pixel order, then NE, SW, SE),
+//                so results are run-to-run deterministic and (fp32, no FMA contraction) bit-identical
+//                to the CPU restatement for sum / avg / linear; `soft` differs only through expf.  Normalisation (softsplat.py:273-290) happens in the
+//                same pass and the output is written exactly once.
+//
+// HBM traffic: in read once + out written once + ~100 B/pixel of list traffic (C-independent).
+// The workspace keeps the library-wide contract (all-zero on entry, all-zero on exit): counters
+// return to zero in step 3, {offset, count} pairs and lists are cleared by a bulk memset after step 4.
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace drba {
+
+constexpr int kGThreads = 256;
+constexpr int kScanThreads = 1024;
+constexpr int kScanPerThread = 4;
+constexpr int kScanBlock = kScanThreads * kScanPerThread;   // 4096 counters per scan block
+
+struct GatherWs {
+    int* count;        // [total]            zero on entry / exit
+    int2* offcnt;      // [total]            {offset, count}
+    int2* entries;     // [4 * total]   {key, corner weight}
+    int* block_sums;   // [nblocks_scan + 1]
+};
+
+__device__ __forceinline__ void corner_targets(const Footprint& f, int H, int W, bool& nw, bool& ne, bool& sw, bool& se)
+{
+    const bool inx0 = f.x0 >= 0 && f.x0 < W, inx1 = f.x0 + 1 >= 0 && f.x0 + 1 < W;
+    const bool iny0 = f.y0 >= 0 && f.y0 < H, iny1 = f.y0 + 1 >= 0 && f.y0 + 1 < H;
+    nw = f.ok && inx0 && iny0; ne = f.ok && inx1 && iny0;
+    sw = f.ok && inx0 && iny1; se = f.ok && inx1 && iny1;
+}
+
+// FILL = false: step 1 (count); FILL = true: step 3 (fill)
+template <bool FILL>
+__global__ void __launch_bounds__(kGThreads)
+splat_list_kernel(const float* __restrict__ flow, int* __restrict__ count, const int2* __restrict__ offcnt,
+                  int2* __restrict__ entries, int N, int H, int W)
+{
+    const size_t HW = (size_t)H * W;
+    const size_t p = (size_t)blockIdx.x * kGThreads + threadIdx.x;
+    if (p >= (size_t)N * HW) return;
+    const int n = (int)(p / HW);
+    const size_t r = p - (size_t)n * HW;
+    const int y = (int)(r / W), x = (int)(r - (size_t)y * W);
+    const float fx = flow[((size_t)n * 2) * HW + r];
+    const float fy = flow[((size_t)n * 2 + 1) * HW + r];
+    const Footprint f = footprint(x, y, fx, fy);
+    bool c[4];
+    corner_targets(f, H, W, c[0], c[1], c[2], c[3]);
+    const long long q = (long long)n * (long long)HW + (long long)f.y0 * W + f.x0;
+    const long long dq[4] = {0, 1, W, (long long)W + 1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!c[k]) continue;
+        const long long t = q + dq[k];
+        if (!FILL) {
+            atomicAdd(count + t, 1);
+        } else {
+            const int slot = atomicSub(count + t, 1) - 1;
+            const float wk = k == 0 ? f.nw : (k == 1 ? f.ne : (k == 2 ? f.sw : f.se));
+            entries[(size_t)offcnt[t].x + slot] = make_int2((int)(((unsigned)k << 29) | (unsigned)r), __float_as_int(wk));
+        }
+    }
+}
+
+// ---- exclusive scan of the counters (three small kernels) ------------------------------------------
+__device__ __forceinline__ int block_exclusive_scan(int v, int* smem_warp, int& total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) smem_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < (kScanThreads / 32) ? smem_warp[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += t;
+        }
+        smem_warp[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    const int warp_off = warp > 0 ? smem_warp[warp - 1] : 0;
+    total = smem_warp[kScanThreads / 32 - 1];
+    __syncthreads();
+    return warp_off + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_block_sums_kernel(const int* __restrict__ count, int* __restrict__ block_sums, size_t total)
+{
+    __shared__ int sw[32];
+    const size_t base = (size_t)blockIdx.x * kScanBlock + (size_t)threadIdx.x * kScanPerThread;
+    int s = 0;
+    if (base + 3 < total) {
+        const int4 v = *reinterpret_cast<const int4*>(count + base);
+        s = v.x + v.y + v.z + v.w;
+    } else {
+        for (int k = 0; k < kScanPerThread; ++k) if (base + k < total) s += count[base + k];
+    }
+    int tot;
+    block_exclusive_scan(s, sw, tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_sums_kernel(int* __restrict__ block_sums, int nblocks)
+{
+    __shared__ int sw[32];
+    int carry = 0;
+    for (int b0 = 0; b0 < nblocks; b0 += kScanThreads) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < nblocks ? block_sums[i] : 0;
+        int tot;
+        const int ex = block_exclusive_scan(v, sw, tot);
+        if (i < nblocks) block_sums[i] = carry + ex;
+        carry += tot;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_write_kernel(const int* __restrict__ count, int* __restrict__ block_sums, int2* __restrict__ offcnt, size_t total)
+{
+    __shared__ int sw[32];
+    const size_t base = (size_t)blockIdx.x * kScanBlock + (size_t)threadIdx.x * kScanPerThread;
+    int v[kScanPerThread];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) { v[k] = base + k < total ? count[base + k] : 0; s += v[k]; }
+    int tot;
+    int ex = block_exclusive_scan(s, sw, tot) + block_sums[blockIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = 0;      // scratch returns to zero
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+        if (base + k < total) offcnt[base + k] = make_int2(ex, v[k]);
+        ex += v[k];
+    }
+}
+
+// ---- step 4: gather -----------------------------------------------------------------------------------
+// List entry = {key = corner << 29 | source pixel, bilinear corner weight}: the fill pass has the footprint at
+// hand, so the gather pass neither re-reads the flow nor recomputes it.
+
+__device__ __forceinline__ void cswap(int& ka, float& wa, int& kb, float& wb) {
+    const bool sw = ka > kb;
+    const int tk = sw ? kb : ka; const float tw = sw ? wb : wa;
+    kb = sw ? ka : kb; wb = sw ? wa : wb;
+    ka = tk; wa = tw;
+}
+
+// Register path: up to 8 list entries per target, sorted with a fixed network; `nmax` is the warp-wide maximum
+// list length, so the entry loop has a warp-uniform trip count (absent entries carry weight 0 and add +0).
+// MODE soft is not bit-comparable with a CPU anyway (expf), so it merges the two weights, contracts to FMA and
+// multiplies by the reciprocal of the denominator; sum / avg / linear keep the reference's operation order.
+template <int MODE, int CCH>
+__device__ __forceinline__ void gather_regs(const float* __restrict__ inb, const float* __restrict__ met, float* __restrict__ outb,
+                                            int2* __restrict__ ent, int n, int nmax, int C, unsigned HW, int eps_mode, int dbg)
+{
+    constexpr int NE = 8;
+    constexpr bool FAST = MODE == DRBA_SPLAT_SOFT;
+    int key[NE]; float wc[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        key[e] = 0x7fffffff; wc[e] = 0.0f;
+        if (e < n) { const int2 v = ent[e]; key[e] = v.x; wc[e] = __int_as_float(v.y); }
+    }
+    if (dbg & 2) {
+    } else if (nmax <= 4) {
+        cswap(key[0], wc[0], key[1], wc[1]); cswap(key[2], wc[2], key[3], wc[3]);
+        cswap(key[0], wc[0], key[2], wc[2]); cswap(key[1], wc[1], key[3], wc[3]);
+        cswap(key[1], wc[1], key[2], wc[2]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < NE; ++r)
+#pragma unroll
+            for (int i = (r & 1); i + 1 < NE; i += 2) cswap(key[i], wc[i], key[i + 1], wc[i + 1]);
+    }
+    unsigned src[NE]; float wg[NE];
+    float den = 0.0f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const bool on = e < n;
+        src[e] = on ? (unsigned)(key[e] & 0x1fffffff) : 0u;
+        wg[e] = 1.0f;
+        if (MODE == DRBA_SPLAT_LINEAR) wg[e] = on ? met[src[e]] : 0.0f;
+        if (MODE == DRBA_SPLAT_SOFT) wg[e] = on ? ((dbg & 4) ? 1.0f : expf(met[src[e]])) : 0.0f;
+        if (MODE != DRBA_SPLAT_SUM) den += wg[e] * wc[e];
+        if (FAST) wc[e] = wg[e] * wc[e];
+    }
+    float rden = 1.0f;
+    if (MODE != DRBA_SPLAT_SUM) { den = splat_den(den, eps_mode); if (FAST) rden = 1.0f / den; }
+    for (int c0 = 0; c0 < C; c0 += CCH) {
+        float acc[CCH];
+#pragma unroll
+        for (int k = 0; k < CCH; ++k) acc[k] = 0.0f;
+        const bool full = c0 + CCH <= C;
+        const unsigned cbase = (unsigned)c0 * HW;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (e < nmax) {        // warp-uniform
+                const unsigned o = cbase + src[e];
+                float t[CCH];
+#pragma unroll
+                for (int k = 0; k < CCH; ++k) t[k] = (full || c0 + k < C) ? inb[o + (unsigned)k * HW] : 0.0f;
+#pragma unroll
+                for (int k = 0; k < CCH; ++k) {
+                    if (FAST) {
+                        acc[k] = fmaf(t[k], wc[e], acc[k]);
+                    } else {
+                        float v = t[k];
+                        if (MODE == DRBA_SPLAT_LINEAR) v = v * wg[e];
+                        acc[k] += v * wc[e];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CCH; ++k)
+            if (full || c0 + k < C)
+                outb[(size_t)(c0 + k) * HW] = MODE == DRBA_SPLAT_SUM ? acc[k] : (FAST ? acc[k] * rden : acc[k] / den);
+    }
+}
+
+template <int MODE, int CCH>
+__global__ void __launch_bounds__(kGThreads)
+splat_gather_kernel(const float* __restrict__ in, const float* __restrict__ metric,
+                    float* __restrict__ out, int2* __restrict__ offcnt, int2* __restrict__ entries,
+                    int N, int C, int H, int W, int eps_mode, int dbg)
+{
+    const size_t HW = (size_t)H * W;
+    const size_t p = (size_t)blockIdx.x * kGThreads + threadIdx.x;
+    const bool live = p < (size_t)N * HW;
+    const size_t pc = live ? p : 0;
+    const int img = (int)(pc / HW);
+    const size_t rp = pc - (size_t)img * HW;
+    int2 oc = make_int2(0, 0);
+    if (live) oc = offcnt[p];
+    const int n = oc.y;
+    int2* ent = entries + (size_t)oc.x;
+    const float* met = metric ? metric + (size_t)img * HW : nullptr;
+    const float* inb = in + (size_t)img * C * HW;
+    float* outb = out + (size_t)img * C * HW + rp;
+    // warp-uniform bound of the register path (lanes with longer lists take the general path below)
+    const int nmax = __reduce_max_sync(0xffffffffu, n <= 8 ? n : 0);
+    if (!live) return;
+
+    if (n <= 8) {
+        gather_regs<MODE, CCH>(inb, met, outb, ent, n, nmax, C, (unsigned)HW, eps_mode, dbg);
+    } else {
+        // rare: many sources land on one target (folds / strong occlusion).  Sort the list in place in global
+        // memory (it is private to this thread; heapsort keeps the worst case at n log n), then stream it once
+        // per channel chunk.
+        auto sift = [&](int root, int end) {
+            const int2 v = ent[root];
+            int i = root;
+            for (;;) {
+                int ch = 2 * i + 1;
+                if (ch >= end) break;
+                if (ch + 1 < end && ent[ch + 1].x > ent[ch].x) ++ch;
+                if (ent[ch].x <= v.x) break;
+                ent[i] = ent[ch];
+                i = ch;
+            }
+            ent[i] = v;
+        };
+        for (int i = n / 2 - 1; i >= 0; --i) sift(i, n);
+        for (int end = n - 1; end > 0; --end) {
+            const int2 t = ent[0]; ent[0] = ent[end]; ent[end] = t;
+            sift(0, end);
+        }
+        float den = 0.0f;
+        if (MODE != DRBA_SPLAT_SUM) {
+            for (int e = 0; e < n; ++e) {
+                const int2 v = ent[e];
+                const int src = v.x & 0x1fffffff;
+                float wg = 1.0f;
+                if (MODE == DRBA_SPLAT_LINEAR) wg = met[src];
+                if (MODE == DRBA_SPLAT_SOFT) wg = expf(met[src]);
+                den += wg * __int_as_float(v.y);
+            }
+            den = splat_den(den, eps_mode);
+        }
+        for (int c0 = 0; c0 < C; c0 += CCH) {
+            float acc[CCH];
+#pragma unroll
+            for (int k = 0; k < CCH; ++k) acc[k] = 0.0f;
+            for (int e = 0; e < n; ++e) {
+                const int2 v = ent[e];
+                const int src = v.x & 0x1fffffff;
+                const float wc = __int_as_float(v.y);
+                float wg = 1.0f;
+                if (MODE == DRBA_SPLAT_LINEAR) wg = met[src];
+                if (MODE == DRBA_SPLAT_SOFT) wg = expf(met[src]);
+                const float* sp = inb + (size_t)c0 * HW + src;
+#pragma unroll
+                for (int k = 0; k < CCH; ++k) {
+                    float t = (c0 + k < C) ? sp[(size_t)k * HW] : 0.0f;
+                    if (MODE == DRBA_SPLAT_LINEAR || MODE == DRBA_SPLAT_SOFT) t = t * wg;
+                    acc[k] += t * wc;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CCH; ++k)
+                if (c0 + k < C) outb[(size_t)(c0 + k) * HW] = MODE != DRBA_SPLAT_SUM ? acc[k] / den : acc[k];
+        }
+    }
+}
+
+static GatherWs carve(void* ws, size_t total)
+{
+    GatherWs g;
+    uint8_t* b = reinterpret_cast<uint8_t*>(ws);
+    const size_t total4 = (total + 3) / 4 * 4;
+    g.count = reinterpret_cast<int*>(b);                         b += total4 * sizeof(int);
+    g.offcnt = reinterpret_cast<int2*>(b);                       b += total4 * sizeof(int2);
+    g.entries = reinterpret_cast<int2*>(b);                      b += 4 * total4 * sizeof(int2);
+    g.block_sums = reinterpret_cast<int*>(b);
+    return g;
+}
+
+size_t splat_gather_workspace_bytes(int N, int H, int W)
+{
+    const size_t total = (size_t)N * H * W;
+    const size_t total4 = (total + 3) / 4 * 4;
+    const size_t nblocks = (total + kScanBlock - 1) / kScanBlock;
+    return total4 * 4 + total4 * 8 + 4 * total4 * 8 + (nblocks + 4) * 4;
+}
+
+int splat_gather_launch(const float* in, const float* flow, const float* metric, float* out,
+                        int N, int C, int H, int W, int mode, int eps_mode, void* ws, cudaStream_t st)
+{
+    const size_t total = (size_t)N * H * W;
+    if (total >= (1ull << 31) || (size_t)H * W >= (1ull << 29) || (size_t)C * H * W >= (1ull << 32)) return DRBA_E_UNSUPPORTED;   // list keys: corner << 29 | pixel index
+    const GatherWs g = carve(ws, total);
+    static int env_dbg = -1;
+    if (env_dbg < 0) { const char* e = getenv("DRBA_SPLAT_DBG"); env_dbg = e ? atoi(e) : 0; }
+    const unsigned grid = cdiv(total, kGThreads);
+    const unsigned nblocks = cdiv(total, kScanBlock);
+    splat_list_kernel<false><<<grid, kGThreads, 0, st>>>(flow, g.count, g.offcnt, g.entries, N, H, W);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    scan_block_sums_kernel<<<nblocks, kScanThreads, 0, st>>>(g.count, g.block_sums, total);
+    scan_sums_kernel<<<1, kScanThreads, 0, st>>>(g.block_sums, (int)nblocks);
+    scan_write_kernel<<<nblocks, kScanThreads, 0, st>>>(g.count, g.block_sums, g.offcnt, total);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    splat_list_kernel<true><<<grid, kGThreads, 0, st>>>(flow, g.count, g.offcnt, g.entries, N, H, W);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+#define GATHER(M) splat_gather_kernel<M, 8><<<grid, kGThreads, 0, st>>>(in, metric, out, g.offcnt, g.entries, N, C, H, W, eps_mode, env_dbg)
+    switch (mode) {
+        case DRBA_SPLAT_SUM: GATHER(DRBA_SPLAT_SUM); break;
+        case DRBA_SPLAT_AVG: GATHER(DRBA_SPLAT_AVG); break;
+        case DRBA_SPLAT_LINEAR: GATHER(DRBA_SPLAT_LINEAR); break;
+        default: GATHER(DRBA_SPLAT_SOFT); break;
+    }
+#undef GATHER
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    // workspace contract (all-zero on exit): the counters restored themselves in the fill pass; the
+    // {offset, count} pairs and the lists are cleared by one bulk memset -- measured 13 us for 88 MB, while
+    // zeroing from inside the gather kernel (a store chasing each load) tripled that kernel's time
+    const size_t total4 = (total + 3) / 4 * 4;
+    const cudaError_t me = cudaMemsetAsync(g.offcnt, 0, total4 * sizeof(int2) + 4 * total4 * sizeof(int2), st);
+    if (me != cudaSuccess) return (int)me;
+    return DRBA_OK;
+}
+
+}  // namespace drba

@@ -41,15 +41,17 @@ def main():
     for (c, h, w, mode, kind) in [(1, 1088, 1920, "avg", "smooth"), (2, 1088, 1920, "avg", "smooth"),
                                   (1, 1088, 1920, "avg", "random"), (3, 544, 960, "soft", "smooth"),
                                   (64, 544, 960, "soft", "smooth"), (64, 544, 960, "soft", "random"),
-                                  (128, 272, 480, "soft", "smooth"), (64, 1152, 1920, "soft", "smooth")]:
+                                  (128, 272, 480, "soft", "smooth"), (64, 1152, 1920, "soft", "smooth"),
+                                  (64, 1152, 1920, "soft", "gentle"), (192, 288, 480, "soft", "gentle")]:
         x = torch.randn((1, c, h, w), device="cuda")
-        flow = smooth_flow(h, w, 8.0, 1) if kind == "smooth" else 8 * torch.randn((1, 2, h, w), device="cuda")
+        flow = (smooth_flow(h, w, 8.0, 1) if kind == "smooth" else smooth_flow(h, w, 2.0, 1) + 6.5 if kind == "gentle"
+                else 8 * torch.randn((1, 2, h, w), device="cuda"))
         metric = torch.randn((1, 1, h, w), device="cuda") if mode == "soft" else None
         nbytes = h * w * 4 * ((c + 2 + (1 if metric is not None else 0)) + c)
-        for variant in (0, 1):
+        for variant in (3, 2, 1):
             ms = timeit(lambda: softsplat(x, flow, metric, mode, _variant=variant), flush=flush)
             print(json.dumps({"op": "softsplat", "C": c, "H": h, "W": w, "mode": mode, "flow": kind,
-                              "variant": "agg_v4" if variant == 0 else "scalar_atomics", "ms": round(ms, 4),
+                              "variant": {3: "gather", 2: "agg_v4", 1: "scalar_atomics"}[variant], "ms": round(ms, 4),
                               "alg_GBps": round(nbytes / ms / 1e6, 1)}), flush=True)
     h, w = 1088, 1920
     f10, f12 = smooth_flow(h, w, 8.0, 2), smooth_flow(h, w, 8.0, 3)
