@@ -36,6 +36,15 @@ SIGNATURES = {
     "drba_resize_bilinear_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
     "drba_frame_ingest_u8": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "drba_frame_egress_u8": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "drba_splat_lists_workspace_bytes": (_Z, [_I, _I]),
+    "drba_splat_lists_build": (_I, [_P, _P, _I, _I, _I, _P, _Z, _P]),
+    "drba_splat_lists_apply_nhwc_f16": (_I, [_P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "drba_splat_lists_apply_nchw_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "drba_splat_lists_release": (_I, [_P, _I, _I, _P]),
+    "drba_pack_planes_nhwc_f16": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _I, _P]),
+    "drba_unpack_nhwc_f16": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _F, _P]),
+    "drba_gmfss_metric_prep": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
+    "drba_gmfss_scale_flow": (_I, [_P, _P, _P, _F, _I, _I, _I, _P, _P, _P]),
     "drba_conv2d_direct_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P,
                                     _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "drba_conv_tc_f16": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
@@ -52,7 +61,9 @@ class ConvLayer(ctypes.Structure):
     _fields_ = [("in_", _P * 2), ("res", _P * 2), ("out", _P * 2), ("w", _P), ("bias", _P), ("slope", _P),
                 ("H", _I), ("W", _I), ("Cin", _I), ("G", _I), ("T", _I), ("dy", _I * 36), ("dx", _I * 36),
                 ("cout_pad", _I), ("cout", _I), ("S", _I), ("OH", _I), ("OW", _I), ("epilogue", _I), ("act", _I),
-                ("out_cstride", _I), ("out_os", _I)]
+                ("out_cstride", _I), ("out_os", _I),
+                ("res2", _P * 2), ("out1", _P * 2), ("out2", _P * 2), ("act1", _I), ("act2", _I),
+                ("slope0", _F), ("slope1", _F), ("slope2", _F)]
 
 
 CONV_MAX_LAYERS = 12

@@ -59,7 +59,12 @@ struct alignas(64) LayerDev {
     const float* bias;      // [G][cout_pad]
     const float* slope;     // PReLU slopes [cout_pad] (act 2) or NULL
     const __half* res[kMaxImages];
+    const __half* res2[kMaxImages];   // second residual input (GridNet three-way sums)
     void* out[kMaxImages];
+    void* out1[kMaxImages];           // optional extra outputs of the same values with their own activation
+    void* out2[kMaxImages];
+    float slope0, slope1, slope2;     // scalar PReLU slopes of out / out1 / out2 (act 4)
+    int act1, act2;
     int OH, OW;
     int Kc, kchunks;        // channels per K step, Cin / Kc
     int S, T, G;
@@ -385,7 +390,8 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             const int row = q * 32 + lane;
             const int ry = row / tile_w, rx = row - ry * tile_w;
             const int OH = L.OH, OW = L.OW, cout = L.cout, cout_pad = L.cout_pad, act = L.act;
-            const int epilogue = L.epilogue, os = L.os, cstride = L.out_cstride;
+            const int epilogue = L.epilogue, os = L.os, cstride = L.out_cstride, act1 = L.act1, act2 = L.act2;
+            const float slope0 = L.slope0, slope1 = L.slope1, slope2 = L.slope2;
             for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount) {
                 const uint32_t buf = tcount & 1u, use = tcount >> 1;
                 if (buf != group) continue;
@@ -399,14 +405,14 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 const float* bias = s_bias + g * cout_pad + nbase;
                 const uint32_t taddr0 = tmem_base + buf * (uint32_t)kMaxNTile + ((uint32_t)(q * 32) << 16);
                 const __half* resb = (epilogue == 0) ? L.res[img] : nullptr;
-                // the residual does not depend on the accumulator: fetch (up to) 64 channels of the first M tile before waiting
-                uint4 rpre[8];
+                // the residual does not depend on the accumulator: fetch (up to) 32 channels of the first M tile before waiting
+                uint4 rpre[4];
                 {
                     const bool v0 = oy_s < OH && ox < OW;
                     if (resb && v0) {
                         const __half* res = resb + ((size_t)oy_s * OW + ox) * cstride + nbase;
 #pragma unroll
-                        for (int h = 0; h < 8; ++h)
+                        for (int h = 0; h < 4; ++h)
                             if (h * 8 < ntile) rpre[h] = reinterpret_cast<const uint4*>(res)[h];
                     }
                 }
@@ -421,7 +427,10 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                         const size_t pix = os == 1 ? (size_t)oy * OW + ox
                                                    : (size_t)(oy * os + (g >> 1)) * (OW * os) + (ox * os + (g & 1));
                         __half* out = reinterpret_cast<__half*>(L.out[img]) + pix * cstride + nbase;
+                        __half* out1 = L.out1[img] ? reinterpret_cast<__half*>(L.out1[img]) + pix * cstride + nbase : nullptr;
+                        __half* out2 = L.out2[img] ? reinterpret_cast<__half*>(L.out2[img]) + pix * cstride + nbase : nullptr;
                         const __half* res = (resb && valid) ? resb + pix * cstride + nbase : nullptr;
+                        const __half* res2 = (L.res2[img] && valid) ? L.res2[img] + pix * cstride + nbase : nullptr;
                         for (int c0 = 0; c0 < ntile; c0 += 32) {
                             uint32_t rr[32];
                             tc_ld16_nowait(taddr + c0, rr);
@@ -446,7 +455,6 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                                     for (int h = 0; h < 2; ++h) {
                                         uint4 rv;
                                         if (mt == 0 && c0 == 0) rv = rpre[hh * 2 + h];
-                                        else if (mt == 0 && c0 == 32) rv = rpre[4 + hh * 2 + h];
                                         else rv = reinterpret_cast<const uint4*>(res + c)[h];
                                         const __half2* hp = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
@@ -456,22 +464,43 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                                         }
                                     }
                                 }
-                                if (act == 1) {
+                                if (res2) {
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.0f ? v[i] : 0.2f * v[i];
-                                } else if (act == 2) {
+                                    for (int h = 0; h < 2; ++h) {
+                                        const uint4 rv = reinterpret_cast<const uint4*>(res2 + c)[h];
+                                        const __half2* hp = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.0f ? v[i] : s_slope[nbase + c + i] * v[i];
-                                } else if (act == 3) {
-#pragma unroll
-                                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+                                        for (int k = 0; k < 4; ++k) {
+                                            const float2 f = __half22float2(hp[k]);
+                                            v[h * 8 + k * 2] += f.x; v[h * 8 + k * 2 + 1] += f.y;
+                                        }
+                                    }
                                 }
-                                uint4 o[2];
-                                __half2* oh = reinterpret_cast<__half2*>(o);
+                                // up to three outputs of the same pre-activation value, each with its own activation
 #pragma unroll
-                                for (int k = 0; k < 8; ++k) oh[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-                                uint4* o4 = reinterpret_cast<uint4*>(out + c);
-                                o4[0] = o[0]; o4[1] = o[1];
+                                for (int oi = 0; oi < 3; ++oi) {
+                                    __half* op = oi == 0 ? out : (oi == 1 ? out1 : out2);
+                                    if (!op) continue;
+                                    const int a = oi == 0 ? act : (oi == 1 ? act1 : act2);
+                                    const float sl = a == 1 ? 0.2f : (a == 3 ? 0.0f : (oi == 0 ? slope0 : (oi == 1 ? slope1 : slope2)));
+                                    float w[16];
+                                    if (a == 0) {
+#pragma unroll
+                                        for (int i = 0; i < 16; ++i) w[i] = v[i];
+                                    } else if (a == 2) {
+#pragma unroll
+                                        for (int i = 0; i < 16; ++i) w[i] = v[i] > 0.0f ? v[i] : s_slope[nbase + c + i] * v[i];
+                                    } else {
+#pragma unroll
+                                        for (int i = 0; i < 16; ++i) w[i] = v[i] > 0.0f ? v[i] : sl * v[i];
+                                    }
+                                    uint4 o[2];
+                                    __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) oh[k] = __floats2half2_rn(w[2 * k], w[2 * k + 1]);
+                                    uint4* o4 = reinterpret_cast<uint4*>(op + c);
+                                    o4[0] = o[0]; o4[1] = o[1];
+                                }
                             }
                         }
                     } else {
@@ -581,7 +610,8 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     if (d.out_os != 1 && d.out_os != 2) return DRBA_E_ARG;
     if (d.epilogue == 0 && ((d.out_os == 1 && G != 1) || (d.out_os == 2 && G != 4))) return DRBA_E_ARG;
     if (d.epilogue == 0 && (d.out_cstride < d.cout_pad || d.out_cstride % 8 != 0)) return DRBA_E_ARG;
-    if (d.act < 0 || d.act > 3 || (d.act == 2 && !d.slope)) return DRBA_E_ARG;
+    if (d.act < 0 || d.act > 4 || (d.act == 2 && !d.slope)) return DRBA_E_ARG;
+    if (d.act1 < 0 || d.act1 > 4 || d.act1 == 2 || d.act2 < 0 || d.act2 > 4 || d.act2 == 2) return DRBA_E_ARG;
     if (d.out_os != 1 && (d.res[0] || d.res[1])) return DRBA_E_ARG;   // residuals only for same-geometry layers
     if (G * d.cout_pad > 512) return DRBA_E_UNSUPPORTED;   // bias / slope tables staged in shared memory
     if (!aligned16(d.w)) return DRBA_E_ALIGN;
@@ -641,7 +671,13 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     L.total_tiles = nimg * G * L.nsplits * L.mtiles;
     L.epilogue = d.epilogue; L.act = d.act; L.bias = d.bias; L.slope = d.slope;
     L.out_cstride = d.out_cstride; L.os = d.out_os;
-    for (int i = 0; i < nimg; ++i) { L.res[i] = (const __half*)d.res[i]; L.out[i] = d.out[i]; }
+    for (int i = 0; i < nimg; ++i) {
+        L.res[i] = (const __half*)d.res[i]; L.res2[i] = (const __half*)d.res2[i];
+        L.out[i] = d.out[i]; L.out1[i] = d.out1[i]; L.out2[i] = d.out2[i];
+        if ((d.res2[i] && !aligned16(d.res2[i])) || (d.out1[i] && !aligned16(d.out1[i])) || (d.out2[i] && !aligned16(d.out2[i]))) return DRBA_E_ALIGN;
+        if (d.epilogue != 0 && (d.res2[i] || d.out1[i] || d.out2[i])) return DRBA_E_ARG;
+    }
+    L.act1 = d.act1; L.act2 = d.act2; L.slope0 = d.slope0; L.slope1 = d.slope1; L.slope2 = d.slope2;
 
     const int b_bytes = ntile * L.Kc * 2;
     const int swz_period = 8 * L.swz_bytes;

@@ -386,4 +386,219 @@ int splat_gather_launch(const float* in, const float* flow, const float* metric,
     return DRBA_OK;
 }
 
+
+// ======================================================================================================
+// Pipeline flavour: lists are built ONCE per (flow, metric) and applied to several tensors -- GMFSS splats the
+// half-resolution image (3 ch) and a 64 / 128 / 192-channel feature map with the same flow and metric
+// (models/model_gmfss/GMFSS.py:96-115).  The sort pass merges the two weights (exp(metric) * bilinear corner)
+// into one float per entry and stores the denominator per target, so the apply kernels are pure streams:
+// no sort, no metric gather, no expf.  Features are NHWC fp16 (the conv engine's layout): one list entry is
+// one contiguous channel vector, read 16 B per thread.
+// ======================================================================================================
+
+template <int MODE>
+__global__ void __launch_bounds__(kGThreads)
+splat_sortw_kernel(const float* __restrict__ metric, const int2* __restrict__ offcnt, int2* __restrict__ entries,
+                   float* __restrict__ den_out, size_t HW)
+{
+    const size_t p = (size_t)blockIdx.x * kGThreads + threadIdx.x;
+    if (p >= HW) return;
+    const int2 oc = offcnt[p];
+    const int n = oc.y;
+    int2* ent = entries + (size_t)oc.x;
+    auto weight = [&](int key) {
+        const int src = key & 0x1fffffff;
+        float wg = 1.0f;
+        if (MODE == DRBA_SPLAT_LINEAR) wg = metric[src];
+        if (MODE == DRBA_SPLAT_SOFT) wg = expf(metric[src]);
+        return wg;
+    };
+    float den = 0.0f;
+    if (n <= 8) {
+        int key[8]; float wc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            key[e] = 0x7fffffff; wc[e] = 0.0f;
+            if (e < n) { const int2 v = ent[e]; key[e] = v.x; wc[e] = __int_as_float(v.y); }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = (r & 1); i + 1 < 8; i += 2) cswap(key[i], wc[i], key[i + 1], wc[i + 1]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (e < n) {
+                const float w = weight(key[e]) * wc[e];
+                den += w;
+                ent[e] = make_int2(key[e] & 0x1fffffff, __float_as_int(w));
+            }
+        }
+    } else {
+        auto sift = [&](int root, int end) {
+            const int2 v = ent[root];
+            int i = root;
+            for (;;) {
+                int ch = 2 * i + 1;
+                if (ch >= end) break;
+                if (ch + 1 < end && ent[ch + 1].x > ent[ch].x) ++ch;
+                if (ent[ch].x <= v.x) break;
+                ent[i] = ent[ch];
+                i = ch;
+            }
+            ent[i] = v;
+        };
+        for (int i = n / 2 - 1; i >= 0; --i) sift(i, n);
+        for (int end = n - 1; end > 0; --end) {
+            const int2 t = ent[0]; ent[0] = ent[end]; ent[end] = t;
+            sift(0, end);
+        }
+        for (int e = 0; e < n; ++e) {
+            const int2 v = ent[e];
+            const float w = weight(v.x) * __int_as_float(v.y);
+            den += w;
+            ent[e] = make_int2(v.x & 0x1fffffff, __float_as_int(w));
+        }
+    }
+    den_out[p] = den;
+}
+
+// thread = (target pixel, group of 8 channels); consecutive lanes = consecutive channel groups of one target
+__global__ void __launch_bounds__(kGThreads)
+splat_apply_nhwc_f16_kernel(const int2* __restrict__ offcnt, const int2* __restrict__ entries, const float* __restrict__ den_in,
+                            const __half* __restrict__ in, int in_cstride, __half* __restrict__ out, int out_cstride, int out_coffset,
+                            int G8, size_t HW, int normalise, int eps_mode, int use_prelu, float slope)
+{
+    const size_t t = (size_t)blockIdx.x * kGThreads + threadIdx.x;
+    if (t >= HW * (size_t)G8) return;
+    const size_t p = t / G8;
+    const int g = (int)(t - p * G8);
+    const int2 oc = offcnt[p];
+    const int2* ent = entries + (size_t)oc.x;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+    const __half* base = in + (size_t)g * 8;
+    for (int e = 0; e < oc.y; ++e) {
+        const int2 v = ent[e];
+        const float w = __int_as_float(v.y);
+        const uint4 q = *reinterpret_cast<const uint4*>(base + (size_t)v.x * in_cstride);
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(h[k]);
+            acc[2 * k] = fmaf(f.x, w, acc[2 * k]);
+            acc[2 * k + 1] = fmaf(f.y, w, acc[2 * k + 1]);
+        }
+    }
+    if (normalise) {
+        const float r = 1.0f / splat_den(den_in[p], eps_mode);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= r;
+    }
+    if (use_prelu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = acc[k] > 0.0f ? acc[k] : slope * acc[k];
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+    *reinterpret_cast<uint4*>(out + p * out_cstride + out_coffset + (size_t)g * 8) = o;
+}
+
+__global__ void __launch_bounds__(kGThreads)
+splat_apply_nchw_f32_kernel(const int2* __restrict__ offcnt, const int2* __restrict__ entries, const float* __restrict__ den_in,
+                            const float* __restrict__ in, float* __restrict__ out, int C, size_t HW, int normalise, int eps_mode)
+{
+    const size_t p = (size_t)blockIdx.x * kGThreads + threadIdx.x;
+    if (p >= HW) return;
+    const int2 oc = offcnt[p];
+    const int2* ent = entries + (size_t)oc.x;
+    const float den = normalise ? splat_den(den_in[p], eps_mode) : 1.0f;
+    for (int c = 0; c < C; ++c) {
+        float acc = 0.0f;
+        for (int e = 0; e < oc.y; ++e) {
+            const int2 v = ent[e];
+            acc += in[(size_t)c * HW + v.x] * __int_as_float(v.y);
+        }
+        out[(size_t)c * HW + p] = normalise ? acc / den : acc;
+    }
+}
+
 }  // namespace drba
+
+using namespace drba;
+
+extern "C" {
+
+size_t drba_splat_lists_workspace_bytes(int H, int W)
+{
+    if (H <= 0 || W <= 0) return 0;
+    return splat_gather_workspace_bytes(1, H, W);
+}
+
+int drba_splat_lists_build(const float* flow, const float* metric, int mode, int H, int W, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!flow || H <= 0 || W <= 0) return DRBA_E_ARG;
+    if (mode < DRBA_SPLAT_SUM || mode > DRBA_SPLAT_SOFT) return DRBA_E_ARG;
+    if ((mode == DRBA_SPLAT_LINEAR || mode == DRBA_SPLAT_SOFT) && !metric) return DRBA_E_ARG;
+    const size_t total = (size_t)H * W;
+    if (total >= (1ull << 29)) return DRBA_E_UNSUPPORTED;
+    if (!ws || ws_bytes < splat_gather_workspace_bytes(1, H, W)) return DRBA_E_WORKSPACE;
+    if (!aligned16(ws)) return DRBA_E_ALIGN;
+    cudaStream_t st = as_stream(stream);
+    const GatherWs g = carve(ws, total);
+    const unsigned grid = cdiv(total, kGThreads);
+    const unsigned nblocks = cdiv(total, kScanBlock);
+    splat_list_kernel<false><<<grid, kGThreads, 0, st>>>(flow, g.count, g.offcnt, g.entries, 1, H, W);
+    scan_block_sums_kernel<<<nblocks, kScanThreads, 0, st>>>(g.count, g.block_sums, total);
+    scan_sums_kernel<<<1, kScanThreads, 0, st>>>(g.block_sums, (int)nblocks);
+    scan_write_kernel<<<nblocks, kScanThreads, 0, st>>>(g.count, g.block_sums, g.offcnt, total);
+    splat_list_kernel<true><<<grid, kGThreads, 0, st>>>(flow, g.count, g.offcnt, g.entries, 1, H, W);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    float* den = reinterpret_cast<float*>(g.count);     // the counters are back at zero: reuse them for the denominators
+    switch (mode) {
+        case DRBA_SPLAT_SUM: splat_sortw_kernel<DRBA_SPLAT_SUM><<<grid, kGThreads, 0, st>>>(metric, g.offcnt, g.entries, den, total); break;
+        case DRBA_SPLAT_AVG: splat_sortw_kernel<DRBA_SPLAT_AVG><<<grid, kGThreads, 0, st>>>(metric, g.offcnt, g.entries, den, total); break;
+        case DRBA_SPLAT_LINEAR: splat_sortw_kernel<DRBA_SPLAT_LINEAR><<<grid, kGThreads, 0, st>>>(metric, g.offcnt, g.entries, den, total); break;
+        default: splat_sortw_kernel<DRBA_SPLAT_SOFT><<<grid, kGThreads, 0, st>>>(metric, g.offcnt, g.entries, den, total); break;
+    }
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+int drba_splat_lists_apply_nhwc_f16(const void* ws, const void* in, int C, int in_cstride, void* out, int out_cstride, int out_coffset,
+                                    int H, int W, int normalise, int eps_mode, int use_prelu, float slope, void* stream)
+{
+    if (!ws || !in || !out || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return DRBA_E_ARG;
+    if (in_cstride < C || in_cstride % 8 != 0 || out_cstride < out_coffset + C || out_cstride % 8 != 0 || out_coffset % 8 != 0) return DRBA_E_ARG;
+    if (!aligned16(in) || !aligned16(out)) return DRBA_E_ALIGN;
+    const size_t total = (size_t)H * W;
+    const GatherWs g = carve(const_cast<void*>(ws), total);
+    const int G8 = C / 8;
+    splat_apply_nhwc_f16_kernel<<<cdiv(total * G8, kGThreads), kGThreads, 0, as_stream(stream)>>>(
+        g.offcnt, g.entries, reinterpret_cast<const float*>(g.count), (const __half*)in, in_cstride, (__half*)out, out_cstride, out_coffset,
+        G8, total, normalise, eps_mode, use_prelu, slope);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+int drba_splat_lists_apply_nchw_f32(const void* ws, const float* in, float* out, int C, int H, int W, int normalise, int eps_mode, void* stream)
+{
+    if (!ws || !in || !out || H <= 0 || W <= 0 || C <= 0) return DRBA_E_ARG;
+    const size_t total = (size_t)H * W;
+    const GatherWs g = carve(const_cast<void*>(ws), total);
+    splat_apply_nchw_f32_kernel<<<cdiv(total, kGThreads), kGThreads, 0, as_stream(stream)>>>(
+        g.offcnt, g.entries, reinterpret_cast<const float*>(g.count), in, out, C, total, normalise, eps_mode);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+int drba_splat_lists_release(void* ws, int H, int W, void* stream)
+{
+    if (!ws || H <= 0 || W <= 0) return DRBA_E_ARG;
+    const cudaError_t e = cudaMemsetAsync(ws, 0, splat_gather_workspace_bytes(1, H, W), as_stream(stream));
+    return e == cudaSuccess ? DRBA_OK : (int)e;
+}
+
+}  // extern "C"

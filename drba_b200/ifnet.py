@@ -236,30 +236,12 @@ class IFNetEngine:
         self._check(rc, "drba_conv_tc_f16")
 
     def _conv_program(self, steps, tag=""):
-        """One persistent launch for a chain of tensor-core conv layers (drba_conv_tc_program_f16).
+        """One persistent launch for a chain of tensor-core conv layers (convnet.run_program).
         steps: [(layer, H, W, ins, outs, OH, OW, out_cstride, ress)] with ins/outs/ress lists of one tensor
         per image (ress may be None); layer i+1 may read what layer i wrote."""
-        nimg = len(steps[0][3])
-        arr = (_lib.ConvLayer * len(steps))()
-        flops = 0.0
-        for c, (layer, H, W, ins, outs, OH, OW, cstride, ress) in zip(arr, steps):
-            for k in range(nimg):
-                c.in_[k] = ptr(ins[k])
-                c.out[k] = ptr(outs[k])
-                c.res[k] = ptr(ress[k]) if ress is not None else None
-            c.w, c.bias, c.slope = ptr(layer.w), ptr(layer.b), ptr(layer.slope)
-            c.H, c.W, c.Cin, c.G, c.T = H, W, layer.cin, layer.G, layer.T
-            n = layer.G * layer.T
-            c.dy[:n] = layer.dy[:n]
-            c.dx[:n] = layer.dx[:n]
-            c.cout_pad, c.cout, c.S, c.OH, c.OW = layer.cout_pad, layer.cout, layer.stride, OH, OW
-            c.epilogue, c.act, c.out_cstride, c.out_os = layer.epilogue, layer.act, cstride, layer.out_os
-            flops += nimg * 2.0 * layer.G * layer.T * layer.cin_real * layer.cout * OH * OW
-        if self._sync is None:
-            self._sync = torch.zeros(2, dtype=torch.int32, device=self.device)
-        with self._launch("conv_tc_f16" + (("/" + tag) if tag else ""), flops=flops):
-            rc = self.L.drba_conv_tc_program_f16(ctypes.addressof(arr), len(steps), nimg, ptr(self._sync), stream_ptr(self.device))
-        self._check(rc, "drba_conv_tc_program_f16")
+        from .convnet import run_program
+        run_program(steps, self.device, tag)
+        self.launches += 1
 
     @staticmethod
     def _nchw(c, h, w):

@@ -87,3 +87,76 @@ def find_rife_weights(explicit=None):
         if c and os.path.isfile(os.path.join(c, "flownet.pkl")):
             return c
     return None
+
+
+# ---- GMFSS (models/model_gmfss: FeatureNet.py:6-33, MetricNet.py:23-43, FusionNet.py:6-105) ------------------
+def _prelu_conv_pairs(prefix, cin, cout, transposed=False):
+    """ResidualBlock / DownsampleBlock / UpsampleBlock parameter shapes (FusionNet.py:6-33)."""
+    first = (cin, cout, 4, 4) if transposed else (cout, cin, 3, 3)
+    return [(f"{prefix}.0.weight", (1,)), (f"{prefix}.1.weight", first), (f"{prefix}.1.bias", (cout,)),
+            (f"{prefix}.2.weight", (1,)), (f"{prefix}.3.weight", (cout, cout, 3, 3)), (f"{prefix}.3.bias", (cout,))]
+
+
+def gmfss_param_shapes():
+    feat, metric, fusion = [], [], []
+    for name, cin, c in (("block1", 3, 64), ("block2", 64, 128), ("block3", 128, 192)):
+        feat += _prelu_conv_pairs(name, cin, c)
+    metric += [("metric_in.weight", (64, 14, 3, 3)), ("metric_in.bias", (64,))]
+    for i in (1, 2, 3):
+        metric += [(f"metric_net{i}.0.weight", (1,)), (f"metric_net{i}.1.weight", (64, 64, 3, 3)), (f"metric_net{i}.1.bias", (64,))]
+    metric += [("metric_out.0.weight", (1,)), ("metric_out.1.weight", (2, 64, 3, 3)), ("metric_out.1.bias", (2,))]
+    for name, cin, c in (("head", 12, 64), ("head1", 128, 64), ("head2", 256, 128), ("head3", 384, 192),
+                         ("01", 64, 64), ("04", 64, 64), ("05", 64, 64), ("11", 128, 128), ("14", 128, 128), ("15", 128, 128),
+                         ("21", 192, 192), ("24", 192, 192), ("25", 192, 192)):
+        fusion += _prelu_conv_pairs("residual_model_" + name, cin, c)
+    fusion += [("residual_model_tail.conv_before_upsample.0.weight", (64, 64, 3, 3)), ("residual_model_tail.conv_before_upsample.0.bias", (64,)),
+               ("residual_model_tail.conv_before_upsample.1.weight", (1,)),
+               ("residual_model_tail.upsample.0.weight", (256, 64, 3, 3)), ("residual_model_tail.upsample.0.bias", (256,)),
+               ("residual_model_tail.conv_last.weight", (3, 64, 3, 3)), ("residual_model_tail.conv_last.bias", (3,))]
+    for name, cin, c in (("10", 64, 128), ("20", 128, 192), ("11", 64, 128), ("21", 128, 192)):
+        fusion += _prelu_conv_pairs("downsample_model_" + name, cin, c)
+    for name, cin, c in (("04", 128, 64), ("14", 192, 128), ("05", 128, 64), ("15", 192, 128)):
+        fusion += _prelu_conv_pairs("upsample_model_" + name, cin, c, transposed=True)
+    return {"feat": feat, "metric": metric, "fusionnet": fusion}
+
+
+def synth_gmfss_state(seed=0):
+    """Seeded stand-in weights of the GMFSS nets (same names / shapes as feat.pkl, metric.pkl, fusionnet.pkl)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(2000 + int(seed))
+    out = {}
+    for net, shapes in gmfss_param_shapes().items():
+        sd = {}
+        for name, shape in shapes:
+            if shape == (1,):
+                v = 0.1 + 0.3 * torch.rand(shape, generator=g)              # PReLU slope
+            elif name.endswith("bias"):
+                v = 0.05 * torch.randn(shape, generator=g)
+            else:
+                transposed = len(shape) == 4 and shape[2] == 4
+                fan_in = (shape[0] * 4) if transposed else shape[1] * shape[2] * shape[3]
+                v = torch.randn(shape, generator=g) * (1.2 / fan_in) ** 0.5
+            sd[name] = v.float()
+        out[net] = sd
+    return out
+
+
+def load_gmfss_state(weights_dir):
+    """feat.pkl / metric.pkl / fusionnet.pkl as models/model_gmfss/GMFSS.py:44-56 loads them (flownet.pkl = GMFlow
+    is handled by the flow estimator)."""
+    out = {}
+    for net in ("feat", "metric", "fusionnet"):
+        raw = torch.load(os.path.join(weights_dir, net + ".pkl"), map_location="cpu")
+        out[net] = {k: v.detach().float().contiguous() for k, v in raw.items()}
+    return out
+
+
+def find_gmfss_weights(explicit=None):
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = [explicit, os.environ.get("DRBA_GMFSS_WEIGHTS"), "weights/train_log_gmfss",
+             os.path.join(here, "weights/train_log_gmfss"), os.path.join(here, "baseline/_ref/weights/train_log_gmfss"),
+             "/root/reference/weights/train_log_gmfss"]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "fusionnet.pkl")):
+            return c
+    return None

@@ -74,6 +74,26 @@ DRBA_API int drba_softsplat_f32_variant(const float* in, const float* flow, cons
                                         void* ws, size_t ws_bytes, int variant, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Splat with reusable lists (csrc/splat_gather.cu): GMFSS forward-warps several tensors with the same
+ * (flow, metric) -- the half-resolution image and a 64/128/192-channel feature map,
+ * models/model_gmfss/GMFSS.py:96-115.  build: count / scan / fill / sort+weights, once per (flow, metric),
+ * batch 1; apply: a pure gather, deterministic; release: re-zeroes the workspace (library contract).
+ *   apply_nhwc_f16: in [H][W][in_cstride] fp16 (C % 8 == 0 channels used), out [H][W][out_cstride] fp16 written
+ *                   at channel offset out_coffset (straight into a concat buffer), optional scalar PReLU on write
+ *   apply_nchw_f32: in / out [C][H][W] fp32
+ * normalise != 0: divide by the splatted weight (avg / linear / soft, softsplat.py:273-290).
+ * ------------------------------------------------------------------------- */
+DRBA_API size_t drba_splat_lists_workspace_bytes(int H, int W);
+DRBA_API int drba_splat_lists_build(const float* flow, const float* metric, int mode, int H, int W,
+                                    void* ws, size_t ws_bytes, void* stream);
+DRBA_API int drba_splat_lists_apply_nhwc_f16(const void* ws, const void* in, int C, int in_cstride,
+                                             void* out, int out_cstride, int out_coffset, int H, int W,
+                                             int normalise, int eps_mode, int use_prelu, float slope, void* stream);
+DRBA_API int drba_splat_lists_apply_nchw_f32(const void* ws, const float* in, float* out, int C, int H, int W,
+                                             int normalise, int eps_mode, void* stream);
+DRBA_API int drba_splat_lists_release(void* ws, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------
  * RIFE.calc_flow's flow inversion, models/rife.py:59-73:
  *   out = 2 * fill(-splat_avg(flow_t0, flow_t0), holes <- max(H, W))
  * flow_t0, out: [N,2,H,W] fp32.  ws >= N*H*W*16 bytes.
@@ -171,7 +191,8 @@ DRBA_API int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
  * after a grid-wide barrier, so layer i+1 may read what layer i wrote (e.g. a whole IFBlock:
  * conv0a, conv0b, 8 x ResConv, lastconv -- IFNet_HDv3.py:84-96).  Up to two independent images
  * (in[k] / res[k] / out[k], same geometry, shared weights) are processed side by side.
- * Field meaning as in drba_conv_tc_f16; act: 0 none, 1 LeakyReLU(0.2), 2 PReLU(slope[cout_pad]), 3 ReLU.
+ * Field meaning as in drba_conv_tc_f16; act: 0 none, 1 LeakyReLU(0.2), 2 PReLU(slope[cout_pad]), 3 ReLU,
+ * 4 PReLU(scalar slope0).
  * sync_ws: 8 zero bytes of device memory (8-byte aligned) owned by the caller, required when
  * nlayers > 1; zero again when the launch completes.  Do not run two programs that share a device
  * concurrently on different streams (each expects to own all SMs between its barriers). */
@@ -186,11 +207,39 @@ typedef struct drba_conv_layer {
     int H, W, Cin, G, T;
     int dy[36], dx[36];
     int cout_pad, cout, S, OH, OW, epilogue, act, out_cstride, out_os;
+    /* epilogue 0 extensions (GMFSS FeatureNet / MetricNet / GridNet, models/model_gmfss/FusionNet.py:6-33:
+     * pre-activation residual blocks whose inputs are consumed raw AND through scalar PReLUs):
+     * value = bias + conv + res + res2; out = act(value); out1 = act1(value); out2 = act2(value).
+     * act / act1 / act2 = 4: scalar PReLU with slope0 / slope1 / slope2.  NULL pointers are skipped. */
+    const void* res2[2];
+    void* out1[2];
+    void* out2[2];
+    int act1, act2;
+    float slope0, slope1, slope2;
 } drba_conv_layer;
 DRBA_API int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nimg, void* sync_ws, void* stream);
 /* debug: while a device buffer of 4096 int64 is registered, CTA 0 of every conv launch writes clock64() stamps
  * of its pipeline events into it (NULL switches tracing off; scripts/trace_conv.py decodes). */
 DRBA_API int drba_conv_tc_debug_trace(void* dev_buf_4096_i64);
+
+/* ---------------------------------------------------------------------------
+ * GMFSS glue (csrc/gmfss.cu).  The conv engine works on NHWC fp16; these are the only places where the NCHW
+ * fp32 API tensors are packed into / unpacked from that layout, fused with the arithmetic around the convs.
+ *   pack_planes : out[y][x][c] = prelu?(scales[c] * planes[c][y][x]), c < nplanes <= 16, zero padding to 16
+ *                 (`planes` / `scales` are HOST arrays of device pointers / floats; scales may be NULL)
+ *   unpack      : NHWC fp16 -> NCHW fp32 planes, optional clamp (GMFSS.py:190)
+ *   metric_prep : MetricNet.forward up to its first conv (MetricNet.py:45-60; fb check geometry.py:87-108)
+ *   scale_flow  : F = t * flow, Z = t * metric resampled to 1/s (s = 1, 2, 4), flow additionally * 1/s
+ *                 (GMFSS.py:88-113); t is a per-pixel map [H][W] or, when tmap == NULL, the scalar
+ * ------------------------------------------------------------------------- */
+DRBA_API int drba_pack_planes_nhwc_f16(const float* const* planes, const float* scales, int nplanes, int H, int W,
+                                       int use_prelu, float slope, void* out, int out_cstride, void* stream);
+DRBA_API int drba_unpack_nhwc_f16(const void* in, int in_cstride, float* out, int C, int H, int W,
+                                  int do_clamp, float lo, float hi, void* stream);
+DRBA_API int drba_gmfss_metric_prep(const float* img0, const float* img1, const float* flow01, const float* flow10,
+                                    void* out_nhwc16, int H, int W, void* stream);
+DRBA_API int drba_gmfss_scale_flow(const float* flow, const float* metric, const float* tmap, float tscalar,
+                                   int H, int W, int s, float* out_flow, float* out_metric, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Fused non-conv stages of IFNet.forward (IFNet_HDv3.py:126-177), batch 1.

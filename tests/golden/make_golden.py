@@ -176,9 +176,67 @@ def gen_rife():
     print("rife_golden.npz:", len(out), "arrays")
 
 
+def gen_gmfss():
+    """GMFSS (models/gmfss.py, models/model_gmfss/*) in fp32 on CPU: per-net outputs and a DRBA window, with the
+    optical flows of the reference's GMFlow stored alongside (the native GMFlow is not built yet; the GPU tests
+    inject these flows).  Two weight sets: seeded synthetic FeatureNet / MetricNet / GridNet weights (reproducible
+    on the GPU box without checkpoints) and the trained ones; GMFlow always runs with its trained weights."""
+    import torch.nn.functional as F
+    from models import gmfss as ref_gmfss
+    from models.model_gmfss.GMFSS import Model
+    from drba_b200.weights import load_gmfss_state, synth_gmfss_state
+
+    torch.set_grad_enabled(False)
+    torch.set_float32_matmul_precision("highest")
+    g = torch.Generator().manual_seed(11)
+    H, W = 128, 192
+
+    def smooth(shape):
+        lo = torch.rand((shape[0], shape[1], shape[2] // 8 + 2, shape[3] // 8 + 2), generator=g)
+        hi = F.interpolate(lo, scale_factor=8, mode="bicubic", align_corners=False)[:, :, 4:4 + shape[2], 4:4 + shape[3]]
+        return (hi + 0.05 * torch.rand(shape, generator=g)).clamp(0, 1)
+
+    base = smooth((1, 3, H + 16, W + 16))
+    I0 = base[:, :, 8:8 + H, 8:8 + W].contiguous()
+    I1 = base[:, :, 7:7 + H, 10:10 + W].contiguous()
+    I2 = base[:, :, 5:5 + H, 13:13 + W].contiguous()
+    out = {"I0": I0.numpy(), "I1": I1.numpy(), "I2": I2.numpy()}
+    wdir = os.path.join(REF, "weights/train_log_gmfss")
+    for tag, state in [("synth", synth_gmfss_state(0)), ("real", load_gmfss_state(wdir))]:
+        m = ref_gmfss.GMFSS.__new__(ref_gmfss.GMFSS)
+        m.model = Model()
+        m.model.load_model(wdir, -1)
+        m.model.feat_ext.load_state_dict(state["feat"], strict=True)
+        m.model.metricnet.load_state_dict(state["metric"], strict=True)
+        m.model.fusionnet.load_state_dict(state["fusionnet"], strict=True)
+        m.model.eval()
+        m.scale = 1.0
+        m.pad_size = 64
+        with torch.inference_mode():
+            r10 = m.model.reuse(I1, I0, 1.0)      # (flow10, flow01, metric10, metric01, feats(I1), feats(I0))
+            r12 = m.model.reuse(I1, I2, 1.0)
+            if tag == "synth":                     # flows depend on GMFlow only
+                out["flow10"], out["flow01"] = r10[0].numpy(), r10[1].numpy()
+                out["flow12"], out["flow21"] = r12[0].numpy(), r12[1].numpy()
+            out[f"{tag}_metric10"], out[f"{tag}_metric01"] = r10[2].numpy(), r10[3].numpy()
+            f1, f2, f3 = r10[4]
+            out[f"{tag}_feat1_sub"] = f1[:, ::4].numpy().astype(np.float16)
+            out[f"{tag}_feat2_sub"] = f2[:, ::8].numpy().astype(np.float16)
+            out[f"{tag}_feat3"] = f3.numpy().astype(np.float16)
+            y = m.model.inference(I1, I0, r10, timestep0=0.3, timestep1=0.7)
+            out[f"{tag}_inf_scalar"] = y.numpy().astype(np.float16)
+            body = ref_gmfss.GMFSS.inference_ts_drba.__wrapped__.__wrapped__
+            o1, reuse = body(m, I0, I1, I2, np.array([0.6, 1.0, 1.4]), None, True)
+            out[f"{tag}_w0_0.6"], out[f"{tag}_w0_1.4"] = o1[0].numpy().astype(np.float16), o1[2].numpy().astype(np.float16)
+    np.savez_compressed(os.path.join(HERE, "gmfss_golden.npz"), **out)
+    print("gmfss_golden.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "rife"]
+    which = sys.argv[1:] or ["ops", "rife", "gmfss"]
     if "ops" in which:
         gen_ops()
     if "rife" in which:
         gen_rife()
+    if "gmfss" in which:
+        gen_gmfss()

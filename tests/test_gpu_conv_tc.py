@@ -139,7 +139,8 @@ def test_conv_program_chain_vs_torch(c, h, w, nimg):
     for rep in range(2):       # second run checks that the barrier words were left zeroed
         eng._conv_program(steps)
     torch.cuda.synchronize()
-    assert int(eng._sync.abs().sum().item()) == 0
+    from drba_b200.convnet import _sync
+    assert int(_sync(torch.device('cuda', torch.cuda.current_device())).abs().sum().item()) == 0
     for k in range(nimg):
         y = _lrelu(F.conv2d(xs[k].float(), w0.half().float(), b0, 2, 1)).half()
         for wi, bi in zip(ws, bs):

@@ -197,3 +197,18 @@ def test_tc_weight_packing_matches_conv():
             acc += torch.einsum("oc,bchw->bohw", layer.w.float()[gph, t], xpad[:, :, 1 + dy:6 + dy, 1 + dx:8 + dx])
         acc = acc + layer.b[gph].view(1, -1, 1, 1)
         torch.testing.assert_close(acc[:, :52], ref[:, :, py::2, px::2], rtol=1e-3, atol=1e-3)
+
+
+def test_gmfss_host_contract_without_gpu():
+    """GMFSS wrapper: CPU device is refused (no fallback); synthetic weights cover every tensor the nets read."""
+    from drba_b200 import _lib
+    from drba_b200.gmfss import GMFSS
+    from drba_b200.weights import gmfss_param_shapes, synth_gmfss_state
+    st = synth_gmfss_state(3)
+    shapes = gmfss_param_shapes()
+    assert {k: len(v) for k, v in shapes.items()} == {"feat": 18, "metric": 14, "fusionnet": 133}
+    for net, lst in shapes.items():
+        for name, shape in lst:
+            assert tuple(st[net][name].shape) == tuple(shape)
+    with pytest.raises(_lib.DrbaError):
+        GMFSS(state=st, device="cpu")
