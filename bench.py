@@ -83,7 +83,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.skip = gpu_index, [], None, 0
+
+    def mark(self):
+        """Samples taken before this call (warm-up) are dropped from the report."""
+        self.skip = len(self.rows)
 
     def start(self):
         try:
@@ -102,6 +106,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        self.rows = self.rows[self.skip:] or self.rows
         sm = [int(r[1]) for r in self.rows if len(r) >= 7 and r[1].isdigit()]
         mx = [int(r[2]) for r in self.rows if len(r) >= 7 and r[2].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -120,6 +125,36 @@ def measured_peaks():
         except Exception:
             pass
     return {"hbm": 6650.0, "tensor": 1590.0, "src": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
+
+
+def softsplat_roofline(dev, peaks):
+    """softsplat(C=64, soft) at 1152x1920 through drba_softsplat_f32: the flow is a smooth field with a
+    constant offset (what DRBA feeds it: flow x timestep); L2 is flushed between runs."""
+    from drba_b200.softsplat import softsplat
+    c, h, w = 64, 1152, 1920
+    g = torch.Generator(device="cpu").manual_seed(1)
+    lo = 2.0 * torch.randn((1, 2, h // 16, w // 16), generator=g)
+    flow = (torch.nn.functional.interpolate(lo, size=(h, w), mode="bilinear", align_corners=False) + 6.5).to(dev)
+    x = torch.randn((1, c, h, w), device=dev)
+    metric = torch.randn((1, 1, h, w), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        softsplat(x, flow, metric, "soft")
+    ts = []
+    for _ in range(7):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        softsplat(x, flow, metric, "soft")
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = sorted(ts)[len(ts) // 2]
+    nbytes = h * w * 4 * ((c + 3) + c)
+    ach = nbytes / ms / 1e6
+    return {"kernel": "softsplat (count/scan/fill/gather, csrc/splat_gather.cu)", "bound": "hbm", "achieved": round(ach, 1),
+            "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4), "ms": round(ms, 4),
+            "workload": "C=64 soft 1152x1920 fp32 NCHW, smooth flow; 6 launches per call", "traffic": None}
 
 
 # ------------------------------------------------------------------------------------------
@@ -215,6 +250,10 @@ def main():
     # warm-up: W windows AND at least `--warmup-seconds` of work, so graph capture, allocator growth and
     # the GPU's clock ramp from idle are all outside the timed region (Wm stays even: the ts pattern
     # alternates, so the timed region starts on the same phase for every run)
+    # the clock sampler (an nvidia-smi child polling every 100 ms) is started BEFORE the warm-up: its start-up
+    # takes a driver lock that stalled the GPU for ~100 ms when it was launched right at the timed region
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     reuse = None
     t_w = time.perf_counter()
     j = 0
@@ -228,8 +267,7 @@ def main():
         j += 1
     Wm_done = j
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark()
     launches0 = _lib.KERNEL_LAUNCHES
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     nout = 0
@@ -321,6 +359,13 @@ def main():
             achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["bytes"] else 0.0
             roof = {"kernel": name, "bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm"],
                     "unit": "GB/s", "frac": round(achieved / peaks["hbm"], 4), "traffic": None}
+        try:      # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_conv_tc_traffic.json")))
+            if name == "conv_tc_f16":
+                roof["traffic"] = tr["dram_bytes_per_launch"]
+                roof["traffic_source"] = "profiles/r1_conv_tc_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+        except Exception:
+            pass
         roof.update({"launches_per_step": round(d["kernels"] / nprof, 1), "avg_launch_us": round(1e3 * d["ms"] / max(d["kernels"], 1), 2),
                      "share_of_step": round(d["ms"] / total_ms, 3), "peak_source": peaks["src"]})
         breakdown = {k: {"ms_per_step": round(v["ms"] / nprof, 4), "kernels_per_step": round(v["kernels"] / nprof, 1),
@@ -337,6 +382,13 @@ def main():
             json.dump({"families": breakdown, "detail": per_tag}, open(args.profile_json, "w"), indent=1)
         print("per-kernel-family breakdown (instrumented pass): " + json.dumps(breakdown), file=sys.stderr)
 
+        # second half of BASELINE.json's metric: softsplat achieved HBM GB/s vs peak, timed live through the
+        # C ABI on the size SURVEY.md 8d names (C = 64, soft, 1152x1920; algorithmic bytes 4*HW*[(C+3)+C])
+        splat = None
+        try:
+            splat = softsplat_roofline(dev, peaks)
+        except Exception as e:       # the headline line must not die on the secondary measurement
+            splat = {"error": str(e)[:200]}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             secs, n_cpu, threads = cpu_port_windows(h, w, 1, 1000)
@@ -358,6 +410,8 @@ def main():
                 "e2e": {"value": round(nout_e_all / (ms_e * 1e-3), 3), "unit": UNIT,
                         "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K)},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+        if splat is not None:
+            line["softsplat_roofline"] = splat
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
