@@ -45,6 +45,20 @@ SIGNATURES = {
     "drba_unpack_nhwc_f16": (_I, [_P, _I, _P, _I, _I, _I, _I, _F, _F, _P]),
     "drba_gmfss_metric_prep": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "drba_gmfss_scale_flow": (_I, [_P, _P, _P, _F, _I, _I, _I, _P, _P, _P]),
+    "drba_gmflow_normalize_img": (_I, [_P, _P, _I, _I, _P]),
+    "drba_gmflow_inorm_stats": (_I, [_P, _I, _I, _I, _P, _P]),
+    "drba_gmflow_inorm_apply": (_I, [_P, _P, _I, _P, _P, _I, _P, _I, _I, _I, _P]),
+    "drba_gmflow_add_position": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "drba_gmflow_window_pack": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "drba_gmflow_softmax_rows": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "drba_gmflow_ln_residual": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "drba_gmflow_soft_readout": (_I, [_P, _I, _I, _I, _P, _I, _I, _F, _P, _P]),
+    "drba_gmflow_local_match": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "drba_gmflow_local_propagate": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "drba_gmflow_warp_feature": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "drba_gmflow_upsampler_input": (_I, [_P, _P, _P, _I, _I, _P]),
+    "drba_gmflow_convex_upsample": (_I, [_P, _P, _P, _I, _I, _P]),
+    "drba_axpby_f32": (_I, [_P, _F, _P, _F, _P, _Z, _P]),
     "drba_conv2d_direct_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P,
                                     _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "drba_conv_tc_f16": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
@@ -63,7 +77,7 @@ class ConvLayer(ctypes.Structure):
                 ("cout_pad", _I), ("cout", _I), ("S", _I), ("OH", _I), ("OW", _I), ("epilogue", _I), ("act", _I),
                 ("out_cstride", _I), ("out_os", _I),
                 ("res2", _P * 2), ("out1", _P * 2), ("out2", _P * 2), ("act1", _I), ("act2", _I),
-                ("slope0", _F), ("slope1", _F), ("slope2", _F)]
+                ("slope0", _F), ("slope1", _F), ("slope2", _F), ("bgemm", _I)]
 
 
 CONV_MAX_LAYERS = 12

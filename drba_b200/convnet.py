@@ -11,21 +11,22 @@ import torch
 from . import _lib
 from ._torch_util import ptr, stream_ptr
 
-ACT_NONE, ACT_LRELU, ACT_PRELU_VEC, ACT_RELU, ACT_PRELU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_LRELU, ACT_PRELU_VEC, ACT_RELU, ACT_PRELU, ACT_GELU = 0, 1, 2, 3, 4, 5
 
 
 class Step:
     """One layer of a program.  ins/outs/res/...: lists with one tensor per image (or None)."""
 
     __slots__ = ("layer", "H", "W", "ins", "outs", "OH", "OW", "cstride", "res", "res2", "out1", "out2",
-                 "act", "act1", "act2", "slope0", "slope1", "slope2")
+                 "act", "act1", "act2", "slope0", "slope1", "slope2", "bgemm")
 
     def __init__(self, layer, H, W, ins, outs, OH, OW, cstride, res=None, res2=None, out1=None, out2=None,
-                 act=None, act1=0, act2=0, slope0=0.0, slope1=0.0, slope2=0.0):
+                 act=None, act1=0, act2=0, slope0=0.0, slope1=0.0, slope2=0.0, bgemm=0):
         self.layer, self.H, self.W, self.ins, self.outs, self.OH, self.OW, self.cstride = layer, H, W, ins, outs, OH, OW, cstride
         self.res, self.res2, self.out1, self.out2 = res, res2, out1, out2
         self.act = layer.act if act is None else act
         self.act1, self.act2, self.slope0, self.slope1, self.slope2 = act1, act2, slope0, slope1, slope2
+        self.bgemm = bgemm
 
 
 _sync_words = {}
@@ -66,6 +67,7 @@ def run_program(steps, device, tag=""):
             c.cout_pad, c.cout, c.S, c.OH, c.OW = layer.cout_pad, layer.cout, layer.stride, s.OH, s.OW
             c.epilogue, c.act, c.out_cstride, c.out_os = layer.epilogue, s.act, s.cstride, layer.out_os
             c.act1, c.act2, c.slope0, c.slope1, c.slope2 = s.act1, s.act2, s.slope0, s.slope1, s.slope2
+            c.bgemm = s.bgemm
             flops += nimg * 2.0 * layer.G * layer.T * layer.cin_real * layer.cout * s.OH * s.OW
         with _lib.launch("conv_tc_f16" + (("/" + tag) if tag else ""), 1, flops=flops):
             rc = L.drba_conv_tc_program_f16(ctypes.addressof(arr), len(chunk), nimg, ptr(_sync(device)), stream_ptr(device))

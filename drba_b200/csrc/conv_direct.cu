@@ -23,7 +23,7 @@ namespace drba {
 constexpr int kTile = 16;      // 16x16 output positions per CTA
 constexpr int kCoT = 16;       // output channels per thread
 constexpr int kCiT = 8;        // input channels staged per iteration
-constexpr int kMaxTaps = 16;
+constexpr int kMaxTaps = 49;      // up to 7x7 (GMFlow backbone.conv1)
 
 struct DirectConvParams {
     const float* in; const float* w; const float* bias; const float* res; float* out;

@@ -71,6 +71,8 @@ struct alignas(64) LayerDev {
     int MT;                 // M tiles per super tile (stacked vertically)
     int KI;                 // pipeline iterations per super tile = T * kchunks
     int resident;           // 1: weights resident in smem for the whole layer
+    int bgemm;              // 1: batched GEMM: the weight rows of a tile are those of batch element oy0 (H = batch)
+    int has_bias;
     int ntile, nsplits, cout_pad, cout;
     int swz_bytes;          // 32 / 64 / 128
     int b_sub;              // bytes of one weight tile (padded to the swizzle period)
@@ -200,7 +202,8 @@ conv_tc_kernel(const __grid_constant__ Program prog)
     auto stage_tables = [&](int li) {
         const LayerDev& L = prog.L[li];
         const int nb = L.G * L.cout_pad;
-        for (int i = threadIdx.x; i < nb; i += kTcThreads) s_bias[i] = L.bias[i];
+        if (L.has_bias)
+            for (int i = threadIdx.x; i < nb; i += kTcThreads) s_bias[i] = L.bias[i];
         if (L.act == 2)
             for (int i = threadIdx.x; i < L.cout_pad; i += kTcThreads) s_slope[i] = L.slope[i];
     };
@@ -310,7 +313,8 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                     int r = idx / mtiles;
                     const int nsplit = r % nsplits; r /= nsplits;
                     const int g = r % G;
-                    const int brow0 = g * T * cout_pad + nsplit * ntile;
+                    int brow0 = g * T * cout_pad + nsplit * ntile;
+                    if (L.bgemm) brow0 += ((idx % mtiles) / tiles_x) * tile_h * MT * cout_pad;    // batch element = output row
                     int tap = 0, kc = 0;
                     for (int it = 0; it < KI; ++it) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -402,7 +406,8 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 const int ty = m / tiles_x;
                 const int oy_s = ty * tile_h * MT + ry, ox = (m - ty * tiles_x) * tile_w + rx;
                 const int nbase = nsplit * ntile;
-                const float* bias = s_bias + g * cout_pad + nbase;
+                const bool has_bias = L.has_bias != 0;
+                const float* bias = s_bias + (has_bias ? g * cout_pad + nbase : 0);
                 const uint32_t taddr0 = tmem_base + buf * (uint32_t)kMaxNTile + ((uint32_t)(q * 32) << 16);
                 const __half* resb = (epilogue == 0) ? L.res[img] : nullptr;
                 // the residual does not depend on the accumulator: fetch (up to) 32 channels of the first M tile before waiting
@@ -444,7 +449,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                                 float v[16];
 #pragma unroll
                                 for (int i = 0; i < 16; i += 4) {
-                                    const float4 b4 = *reinterpret_cast<const float4*>(bias + c + i);
+                                    const float4 b4 = has_bias ? *reinterpret_cast<const float4*>(bias + c + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                                     v[i] = __uint_as_float(rr[hh * 16 + i]) + b4.x;
                                     v[i + 1] = __uint_as_float(rr[hh * 16 + i + 1]) + b4.y;
                                     v[i + 2] = __uint_as_float(rr[hh * 16 + i + 2]) + b4.z;
@@ -490,6 +495,9 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                                     } else if (a == 2) {
 #pragma unroll
                                         for (int i = 0; i < 16; ++i) w[i] = v[i] > 0.0f ? v[i] : s_slope[nbase + c + i] * v[i];
+                                    } else if (a == 5) {      // exact GELU (nn.GELU default)
+#pragma unroll
+                                        for (int i = 0; i < 16; ++i) w[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
                                     } else {
 #pragma unroll
                                         for (int i = 0; i < 16; ++i) w[i] = v[i] > 0.0f ? v[i] : sl * v[i];
@@ -599,7 +607,8 @@ static CUtensorMapSwizzle swz_enum(int bytes)
 static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTiledFn encode)
 {
     const int H = d.H, W = d.W, Cin = d.Cin, G = d.G, T = d.T, S = d.S, OH = d.OH, OW = d.OW;
-    if (!d.w || !d.bias) return DRBA_E_ARG;
+    if (!d.w) return DRBA_E_ARG;
+    if (!d.bias && d.epilogue != 0) return DRBA_E_ARG;
     if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || Cin <= 0 || Cin % 16 != 0) return DRBA_E_ARG;
     if (G < 1 || G > kMaxGroups || T < 1 || T > kMaxTapsTc) return DRBA_E_ARG;
     if (S != 1 && S != 2) return DRBA_E_ARG;
@@ -610,10 +619,11 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     if (d.out_os != 1 && d.out_os != 2) return DRBA_E_ARG;
     if (d.epilogue == 0 && ((d.out_os == 1 && G != 1) || (d.out_os == 2 && G != 4))) return DRBA_E_ARG;
     if (d.epilogue == 0 && (d.out_cstride < d.cout_pad || d.out_cstride % 8 != 0)) return DRBA_E_ARG;
-    if (d.act < 0 || d.act > 4 || (d.act == 2 && !d.slope)) return DRBA_E_ARG;
+    if (d.act < 0 || d.act > 5 || (d.act == 2 && !d.slope)) return DRBA_E_ARG;
     if (d.act1 < 0 || d.act1 > 4 || d.act1 == 2 || d.act2 < 0 || d.act2 > 4 || d.act2 == 2) return DRBA_E_ARG;
     if (d.out_os != 1 && (d.res[0] || d.res[1])) return DRBA_E_ARG;   // residuals only for same-geometry layers
-    if (G * d.cout_pad > 512) return DRBA_E_UNSUPPORTED;   // bias / slope tables staged in shared memory
+    if (d.bias && G * d.cout_pad > 512) return DRBA_E_UNSUPPORTED;   // bias / slope tables staged in shared memory
+    if (d.bgemm && (G != 1 || T != 1 || S != 1 || d.epilogue != 0 || d.bias)) return DRBA_E_ARG;
     if (!aligned16(d.w)) return DRBA_E_ALIGN;
     for (int i = 0; i < nimg; ++i) {
         if (!d.in[i] || !d.out[i]) return DRBA_E_ARG;
@@ -622,6 +632,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
 
     memset(&L, 0, sizeof(L));
     L.OH = OH; L.OW = OW; L.S = S; L.T = T; L.G = G;
+    L.bgemm = d.bgemm ? 1 : 0; L.has_bias = d.bias ? 1 : 0;
     L.Kc = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16);
     L.kchunks = Cin / L.Kc;
     L.swz_bytes = L.Kc * 2;
@@ -651,6 +662,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
         for (int i = 0; i < 5; ++i) {
             const int sh = shapes[i][1] * mt;
             if (sh > 256) continue;
+            if (d.bgemm && sh != 1) continue;      // a tile must not straddle batch elements
             const long nt = (long)((OW + shapes[i][0] - 1) / shapes[i][0]) * ((OH + sh - 1) / sh);
             const long cost = nt * mt;       // covered M tiles (waste included)
             // prefer the larger super tile unless it wastes > 6 % more coverage
@@ -684,7 +696,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     L.b_sub = (b_bytes + swz_period - 1) / swz_period * swz_period;
     L.KI = T * L.kchunks;
     // weights resident in shared memory when every tile of the layer fits
-    L.resident = ((long)G * L.nsplits * L.KI * L.b_sub <= (long)kBRegion) ? 1 : 0;
+    L.resident = (!d.bgemm && (long)G * L.nsplits * L.KI * L.b_sub <= (long)kBRegion) ? 1 : 0;
     {
         static int env_res = -1;
         if (env_res < 0) { const char* e = getenv("DRBA_TC_RESIDENT"); env_res = e ? atoi(e) : 1; }
@@ -705,7 +717,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
         if (r != CUDA_SUCCESS) return DRBA_E_UNSUPPORTED;
     }
     {
-        const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)G * T * d.cout_pad};
+        const cuuint64_t dims[2] = {(cuuint64_t)Cin, d.bgemm ? (cuuint64_t)H * d.cout_pad : (cuuint64_t)G * T * d.cout_pad};
         const cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
         const cuuint32_t box[2] = {(cuuint32_t)L.Kc, (cuuint32_t)ntile};
         const cuuint32_t estr[2] = {1, 1};

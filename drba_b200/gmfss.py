@@ -6,9 +6,10 @@ front end), the per-scale flow and metric scaling, all forward splats (one list 
 scale), applied to the image and to the NHWC fp16 feature map, written straight into GridNet's concat
 buffers with the head PReLU fused), GridNet, calc_drm_gmfss.
 
-NOT built in this round: GMFlow (row a-9).  `flow_estimator(img_a, img_b) -> flow_ab [1,2,h,w]` must be
-supplied by the caller; without one `Model.reuse` raises DrbaError -- there is no silent fallback.  The
-parity tests inject flows produced by the reference's GMFlow (tests/golden) or the oracle restatement.
+GMFlow (row a-9) is `drba_b200.gmflow.GMFlow` (tcgen05 conv / batched-GEMM programs + csrc/gmflow.cu); it is built
+from `flownet.pkl` (state["flownet"]).  A different `flow_estimator(img_a, img_b) -> flow_ab [1,2,h,w]` can be
+injected (the component parity tests inject the reference GMFlow's flows from tests/golden); with neither,
+`Model.reuse` raises DrbaError -- there is no silent fallback.
 
 Differences a caller can observe: frames are returned as fp32 (the reference returns the autocast dtype);
 the entries of `reuse` holding features are tuples of NHWC fp16 tensors (opaque to infer.py).
@@ -45,6 +46,9 @@ class Model:
         self.feat_ext = FeatureNet(state["feat"], self.device)
         self.metricnet = MetricNet(state["metric"], self.device)
         self.fusionnet = GridNet(state["fusionnet"], self.device)
+        if flow_estimator is None and "flownet" in state:
+            from .gmflow import GMFlow
+            flow_estimator = GMFlow(state["flownet"], self.device)      # models/model_gmfss/GMFSS.py:21 self.flownet
         self.flow_estimator = flow_estimator
         self.version = 3.9
 
@@ -52,8 +56,8 @@ class Model:
     def reuse(self, img0, img1, scale):
         require_cuda(img0, img1)
         if self.flow_estimator is None:
-            raise _lib.DrbaError("GMFlow (SURVEY.md 8a-9) is not built yet: construct the model with "
-                                 "flow_estimator=callable(img_a, img_b) -> flow_ab; there is no fallback")
+            raise _lib.DrbaError("no GMFlow weights (state['flownet'] / flownet.pkl) and no flow_estimator=callable(img_a, img_b) "
+                                 "-> flow_ab were given; there is no fallback")
         feat_ext0, feat_ext1 = self.feat_ext([img0, img1])
         img0h = resize_bilinear(img0, scale_factor=0.5)
         img1h = resize_bilinear(img1, scale_factor=0.5)

@@ -142,11 +142,13 @@ def synth_gmfss_state(seed=0):
 
 
 def load_gmfss_state(weights_dir):
-    """feat.pkl / metric.pkl / fusionnet.pkl as models/model_gmfss/GMFSS.py:44-56 loads them (flownet.pkl = GMFlow
-    is handled by the flow estimator)."""
+    """feat.pkl / metric.pkl / fusionnet.pkl / flownet.pkl (GMFlow) as models/model_gmfss/GMFSS.py:44-56 loads them."""
     out = {}
-    for net in ("feat", "metric", "fusionnet"):
-        raw = torch.load(os.path.join(weights_dir, net + ".pkl"), map_location="cpu")
+    for net in ("feat", "metric", "fusionnet", "flownet"):
+        path = os.path.join(weights_dir, net + ".pkl")
+        if net == "flownet" and not os.path.isfile(path):
+            continue
+        raw = torch.load(path, map_location="cpu")
         out[net] = {k: v.detach().float().contiguous() for k, v in raw.items()}
     return out
 

@@ -192,7 +192,7 @@ DRBA_API int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
  * conv0a, conv0b, 8 x ResConv, lastconv -- IFNet_HDv3.py:84-96).  Up to two independent images
  * (in[k] / res[k] / out[k], same geometry, shared weights) are processed side by side.
  * Field meaning as in drba_conv_tc_f16; act: 0 none, 1 LeakyReLU(0.2), 2 PReLU(slope[cout_pad]), 3 ReLU,
- * 4 PReLU(scalar slope0).
+ * 4 PReLU(scalar slope0), 5 GELU (erf).
  * sync_ws: 8 zero bytes of device memory (8-byte aligned) owned by the caller, required when
  * nlayers > 1; zero again when the launch completes.  Do not run two programs that share a device
  * concurrently on different streams (each expects to own all SMs between its barriers). */
@@ -216,6 +216,10 @@ typedef struct drba_conv_layer {
     void* out2[2];
     int act1, act2;
     float slope0, slope1, slope2;
+    /* batched GEMM (GMFlow attention / correlation, models/gmflow/transformer.py:8-17, matching.py:7-43):
+     * in = A [H = batch][W = M rows][Cin = K], w = B [batch][cout_pad rows][K] (K-major), G = T = S = 1, no bias:
+     * out[b][m][n] = sum_k A[b][m][k] * B[b][n][k].  bias may be NULL for any epilogue-0 layer. */
+    int bgemm;
 } drba_conv_layer;
 DRBA_API int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nimg, void* sync_ws, void* stream);
 /* debug: while a device buffer of 4096 int64 is registered, CTA 0 of every conv launch writes clock64() stamps
@@ -240,6 +244,42 @@ DRBA_API int drba_gmfss_metric_prep(const float* img0, const float* img1, const 
                                     void* out_nhwc16, int H, int W, void* stream);
 DRBA_API int drba_gmfss_scale_flow(const float* flow, const float* metric, const float* tmap, float tscalar,
                                    int H, int W, int s, float* out_flow, float* out_metric, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * GMFlow glue (csrc/gmflow.cu; models/gmflow/*).  Every dense contraction of GMFlow runs on
+ * drba_conv_tc_program_f16 (convs, linears as 1x1 convs, attention / correlation as batched GEMMs); these are
+ * the stages in between.  Token tensors are NHWC fp16 [B][h][w][C]; flows are planar fp32 [2][h][w].
+ *   normalize_img   : (img - mean) / std, utils.py:58-70
+ *   inorm_stats/apply: InstanceNorm2d (eps 1e-5, no affine) of backbone.py:14-43; stats = double [C][2] (sum, sum^2),
+ *                     zero on entry; apply: out = relu?( skip(+its own IN) + relu?(IN(x)) )
+ *   add_position    : windowed sine position encoding (utils.py:73-94), pos = fp32 [wh][ww][C]
+ *   window_pack     : split into k x k attention windows, optionally after the half-window roll of the shifted
+ *                     blocks (transformer.py:74-84); dst [B*k*k][rows_pad][C] or transposed [B*k*k][C][rows_pad]
+ *   softmax_rows    : in-place row softmax of the scores [nwin][Lw][ld] incl. the shift mask (transformer.py:20-45)
+ *   ln_residual     : out = src + LayerNorm(m) (m in window order when k > 0), or cat = [src | LayerNorm(m)]
+ *   soft_readout    : out[row] = sum_j softmax(scale * S[row])_j * val[j] (val NULL: grid coordinates), matching.py:31-41
+ *   local_match     : (2r+1)^2 correlation soft-argmax, matching.py:46-89;  local_propagate: transformer.py:366-409
+ *   warp_feature    : bilinear zero-padded warp of a feature map (gmflow.py:117-123)
+ *   upsampler_input / convex_upsample: gmflow.py:68-90 around the two-conv mask head
+ * ------------------------------------------------------------------------- */
+DRBA_API int drba_gmflow_normalize_img(const float* in, float* out, int H, int W, void* stream);
+DRBA_API int drba_gmflow_inorm_stats(const void* x, int C, int H, int W, double* stats_zeroed, void* stream);
+DRBA_API int drba_gmflow_inorm_apply(const void* x, const double* stats, int relu_x, const void* skip, const double* skip_stats,
+                                     int final_relu, void* out, int C, int H, int W, void* stream);
+DRBA_API int drba_gmflow_add_position(void* x, const float* pos, int B, int h, int w, int wh, int ww, int C, void* stream);
+DRBA_API int drba_gmflow_window_pack(const void* src, void* dst, int B, int h, int w, int C, int k, int shifted, int rows_pad,
+                                     int transposed, void* stream);
+DRBA_API int drba_gmflow_softmax_rows(void* S, int nwin_total, int Lw, int ld, int shifted, int k, int h, int w, void* stream);
+DRBA_API int drba_gmflow_ln_residual(const void* src, const void* m, const float* gamma, const float* beta, void* out,
+                                     int B, int h, int w, int C, int k, int shifted, int rows_pad, int cat, void* stream);
+DRBA_API int drba_gmflow_soft_readout(const void* S, int rows, int cols, int ld, const float* val, int w, int subtract_grid,
+                                      float scale, float* out, void* stream);
+DRBA_API int drba_gmflow_local_match(const void* f0, const void* f1, int h, int w, int C, int radius, float* flow, void* stream);
+DRBA_API int drba_gmflow_local_propagate(const void* q, const void* kmap, const float* flow, int h, int w, int C, float* out, void* stream);
+DRBA_API int drba_gmflow_warp_feature(const void* f, const float* flow, void* out, int h, int w, int C, void* stream);
+DRBA_API int drba_gmflow_upsampler_input(const float* flow, const void* feat, void* out144, int h, int w, void* stream);
+DRBA_API int drba_gmflow_convex_upsample(const void* mask144, const float* flow, float* out, int h, int w, void* stream);
+DRBA_API int drba_axpby_f32(const float* a, float alpha, const float* b, float beta, float* out, size_t n, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Fused non-conv stages of IFNet.forward (IFNet_HDv3.py:126-177), batch 1.

@@ -42,6 +42,19 @@ def main():
     lo = 4.0 * torch.randn((1, 2, H // 32, W // 32), generator=g)
     flow = torch.nn.functional.interpolate(lo, size=(H // 2, W // 2), mode="bilinear", align_corners=False).to(dev)
     m = GMFSS(state=state, device=dev, flow_estimator=lambda a, b: flow)
+    if "flownet" in state:
+        from drba_b200.gmflow import GMFlow
+        from drba_b200.ops import resize_bilinear as _rb
+        gm = GMFlow(state["flownet"], dev)
+        a_h, b_h = _rb(frames[0], scale_factor=0.5), _rb(frames[1], scale_factor=0.5)
+        out["gmflow_one_direction_ms"] = round(timeit(lambda: gm(a_h, b_h), n=5), 3)
+        with _lib.LaunchProfiler() as prof:
+            gm(a_h, b_h)
+            fam = prof.summary()
+        conv = [v for k, v in fam.items() if k.startswith("conv_tc")]
+        out["gmflow_conv_breakdown_ms"] = {k: round(v["ms"], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+        out["gmflow_engine_TFLOPs"] = round(sum(v["flops"] for v in conv) / sum(v["ms"] for v in conv) / 1e9, 1)
+        out["gmflow_engine_GFLOP"] = round(sum(v["flops"] for v in conv) / 1e9, 1)
     out = {"weights": "trained" if w else "synthetic", "net_input": [H, W]}
     out["featurenet_2frames_ms"] = round(timeit(lambda: m.model.feat_ext([frames[0], frames[1]])), 3)
     r = m.model.reuse(frames[1], frames[0], 1.0)
