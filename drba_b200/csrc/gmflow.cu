@@ -34,58 +34,86 @@ normalize_img_kernel(const float* __restrict__ in, float* __restrict__ out, size
 }
 
 // ---- InstanceNorm2d (affine = False, eps 1e-5) over NHWC fp16 (backbone.py:14-43) --------------------
-// stats[c] = {sum, sum of squares} in double; one block handles a strip of pixels, threads own channels
+// stats[c] = {sum, sum of squares} in double.  A thread owns a group of 8 channels (one 16 B load per pixel) and
+// walks a strip of pixels; partial sums meet in shared memory, one double atomic pair per channel and block.
 __global__ void __launch_bounds__(kGfThreads)
 inorm_stats_kernel(const __half* __restrict__ x, int C, size_t HW, int pix_per_block, double* __restrict__ stats)
 {
+    const int G = C / 8;                         // channel groups
+    const int R = kGfThreads / G;                // pixel lanes
+    const int g = threadIdx.x % G, r = threadIdx.x / G;
     const size_t p0 = (size_t)blockIdx.x * pix_per_block;
     const size_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
-    // thread t handles channel (t % C) of pixels p0 + t / C, stepping by kGfThreads / C pixels
-    const int lanes = kGfThreads / C > 0 ? kGfThreads / C : 1;
-    const int c = threadIdx.x % C, r = threadIdx.x / C;
-    float s = 0.0f, ss = 0.0f;
-    if (r < lanes)
-        for (size_t p = p0 + r; p < p1; p += lanes) {
-            const float v = __half2float(x[p * C + c]);
-            s += v; ss += v * v;
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.0f; ss[j] = 0.0f; }
+    if (r < R)
+        for (size_t p = p0 + r; p < p1; p += R) {
+            const uint4 v = *reinterpret_cast<const uint4*>(x + p * C + g * 8);
+            const __half2* hp = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(hp[j]);
+                s[2 * j] += f.x; ss[2 * j] += f.x * f.x; s[2 * j + 1] += f.y; ss[2 * j + 1] += f.y * f.y;
+            }
         }
-    __shared__ float sh_s[kGfThreads], sh_ss[kGfThreads];
-    sh_s[threadIdx.x] = s; sh_ss[threadIdx.x] = ss;
+    __shared__ float sh[2][128];
+    for (int i = threadIdx.x; i < 2 * 128; i += kGfThreads) (&sh[0][0])[i] = 0.0f;
+    __syncthreads();
+    if (r < R) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&sh[0][g * 8 + j], s[j]); atomicAdd(&sh[1][g * 8 + j], ss[j]); }
+    }
     __syncthreads();
     if (threadIdx.x < C) {
-        float a = 0.0f, b = 0.0f;
-        for (int k = 0; k < lanes; ++k) { a += sh_s[k * C + threadIdx.x]; b += sh_ss[k * C + threadIdx.x]; }
-        atomicAdd(stats + 2 * threadIdx.x, (double)a);
-        atomicAdd(stats + 2 * threadIdx.x + 1, (double)b);
+        atomicAdd(stats + 2 * threadIdx.x, (double)sh[0][threadIdx.x]);
+        atomicAdd(stats + 2 * threadIdx.x + 1, (double)sh[1][threadIdx.x]);
     }
 }
 
-// out = relu?( [skip (raw or IN'd)] + relu?(IN(x)) ), everything NHWC fp16
+// out = relu?( [skip (raw or IN'd)] + relu?(IN(x)) ), everything NHWC fp16; a thread handles 8 channels
 __global__ void __launch_bounds__(kGfThreads)
 inorm_apply_kernel(const __half* __restrict__ x, const double* __restrict__ stats, int relu_x,
                    const __half* __restrict__ skip, const double* __restrict__ skip_stats, int final_relu,
-                   __half* __restrict__ out, int C, size_t HW, double* __restrict__ clear_a, double* __restrict__ clear_b)
+                   __half* __restrict__ out, int C, size_t HW)
 {
-    const size_t i = (size_t)blockIdx.x * kGfThreads + threadIdx.x;
-    if (i >= HW * (size_t)C) return;
-    const int c = (int)(i % C);
-    const double n = (double)HW;
-    const double m = stats[2 * c] / n;
-    const double var = stats[2 * c + 1] / n - m * m;
-    float v = (__half2float(x[i]) - (float)m) * rsqrtf((float)(var > 0.0 ? var : 0.0) + 1e-5f);
-    if (relu_x) v = fmaxf(v, 0.0f);
-    if (skip) {
-        float sk = __half2float(skip[i]);
+    __shared__ float s_mean[128], s_rstd[128], k_mean[128], k_rstd[128];
+    if (threadIdx.x < C) {
+        const double n = (double)HW;
+        const int c = threadIdx.x;
+        const double m = stats[2 * c] / n, var = stats[2 * c + 1] / n - m * m;
+        s_mean[c] = (float)m; s_rstd[c] = rsqrtf((float)(var > 0.0 ? var : 0.0) + 1e-5f);
         if (skip_stats) {
-            const double sm = skip_stats[2 * c] / n;
-            const double sv = skip_stats[2 * c + 1] / n - sm * sm;
-            sk = (sk - (float)sm) * rsqrtf((float)(sv > 0.0 ? sv : 0.0) + 1e-5f);
+            const double sm = skip_stats[2 * c] / n, sv2 = skip_stats[2 * c + 1] / n - sm * sm;
+            k_mean[c] = (float)sm; k_rstd[c] = rsqrtf((float)(sv2 > 0.0 ? sv2 : 0.0) + 1e-5f);
         }
-        v += sk;
     }
-    if (final_relu) v = fmaxf(v, 0.0f);
-    out[i] = __float2half_rn(v);
-    (void)clear_a; (void)clear_b;
+    __syncthreads();
+    const size_t i = (size_t)blockIdx.x * kGfThreads + threadIdx.x;
+    const int G = C / 8;
+    if (i >= HW * (size_t)G) return;
+    const int g = (int)(i % G);
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + i * 8);
+    const __half* xh = reinterpret_cast<const __half*>(&xv);
+    uint4 sv = make_uint4(0, 0, 0, 0);
+    if (skip) sv = *reinterpret_cast<const uint4*>(skip + i * 8);
+    const __half* sh = reinterpret_cast<const __half*>(&sv);
+    uint4 ov;
+    __half* oh = reinterpret_cast<__half*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        float v = (__half2float(xh[j]) - s_mean[c]) * s_rstd[c];
+        if (relu_x) v = fmaxf(v, 0.0f);
+        if (skip) {
+            float sk = __half2float(sh[j]);
+            if (skip_stats) sk = (sk - k_mean[c]) * k_rstd[c];
+            v += sk;
+        }
+        if (final_relu) v = fmaxf(v, 0.0f);
+        oh[j] = __float2half_rn(v);
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = ov;
 }
 
 // ---- windowed sine position (utils.py:73-94) added in place ------------------------------------------
@@ -141,38 +169,64 @@ __device__ __forceinline__ int shift_region(int l, int win, int k, int wh, int w
     return ry * 3 + rx;
 }
 
+// grid = (ceil(Lw / 8), windows): the 8 warps of a block take 8 rows of ONE window; the region id of every key
+// token (shifted blocks) is tabulated once per block; a row is read once with 16 B loads (a lane owns 8
+// consecutive columns of every 256-column slab) and written once.
+constexpr int kSoftmaxMaxCols = 2048;
+template <int NS>      // 256-column slabs per row
 __global__ void __launch_bounds__(kGfThreads)
 softmax_rows_kernel(__half* __restrict__ S, int nwin_total, int Lw, int ld, int shifted, int k, int wh, int ww, int h, int w)
 {
-    const int warp = (int)(((size_t)blockIdx.x * kGfThreads + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (warp >= nwin_total * Lw) return;
-    const int win_b = warp / Lw, q = warp - win_b * Lw, win = win_b % (k * k);
-    __half* row = S + ((size_t)win_b * Lw + q) * ld;
+    __shared__ unsigned char region[kSoftmaxMaxCols];
+    const int win_b = blockIdx.y, win = win_b % (k * k);
     const int sh = wh / 2, sw = ww / 2;
-    const int rq = shifted ? shift_region(q, win, k, wh, ww, h, w, sh, sw) : 0;
+    if (shifted) {
+        for (int j = threadIdx.x; j < Lw; j += kGfThreads) region[j] = (unsigned char)shift_region(j, win, k, wh, ww, h, w, sh, sw);
+        __syncthreads();
+    }
+    const int q = blockIdx.x * (kGfThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= Lw) return;
+    __half* row = S + ((size_t)win_b * Lw + q) * ld;
+    const int rq = shifted ? region[q] : 0;
+    float v[NS * 8];
     float mx = -3.0e38f;
-    for (int j = lane; j < Lw; j += 32) {
-        float v = __half2float(row[j]);
-        if (shifted && shift_region(j, win, k, wh, ww, h, w, sh, sw) != rq) v += -100.0f;
-        mx = fmaxf(mx, v);
+#pragma unroll
+    for (int s8 = 0; s8 < NS; ++s8) {
+        const int j0 = s8 * 256 + lane * 8;
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (j0 < ld) raw = *reinterpret_cast<const uint4*>(row + j0);        // ld is a multiple of 16
+        const __half* hv = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int j = j0 + e;
+            float t = -3.0e38f;
+            if (j < Lw) {
+                t = __half2float(hv[e]);
+                if (shifted && region[j] != rq) t += -100.0f;
+            }
+            v[s8 * 8 + e] = t;
+            mx = fmaxf(mx, t);
+        }
     }
     mx = warp_max(mx);
     float sum = 0.0f;
-    for (int j = lane; j < Lw; j += 32) {
-        float v = __half2float(row[j]);
-        if (shifted && shift_region(j, win, k, wh, ww, h, w, sh, sw) != rq) v += -100.0f;
-        sum += __expf(v - mx);
+#pragma unroll
+    for (int i = 0; i < NS * 8; ++i) {
+        v[i] = v[i] > -1.0e38f ? __expf(v[i] - mx) : 0.0f;
+        sum += v[i];
     }
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
-    for (int j = lane; j < ld; j += 32) {
-        float o = 0.0f;
-        if (j < Lw) {
-            float v = __half2float(row[j]);
-            if (shifted && shift_region(j, win, k, wh, ww, h, w, sh, sw) != rq) v += -100.0f;
-            o = __expf(v - mx) * inv;
+#pragma unroll
+    for (int s8 = 0; s8 < NS; ++s8) {
+        const int j0 = s8 * 256 + lane * 8;
+        if (j0 < ld) {
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[s8 * 8 + 2 * e] * inv, v[s8 * 8 + 2 * e + 1] * inv);
+            *reinterpret_cast<uint4*>(row + j0) = o;
         }
-        row[j] = __float2half_rn(o);
     }
 }
 
@@ -443,9 +497,11 @@ int drba_gmflow_normalize_img(const float* in, float* out, int H, int W, void* s
 
 int drba_gmflow_inorm_stats(const void* x, int C, int H, int W, double* stats_zeroed, void* stream)
 {
-    if (!x || !stats_zeroed || C <= 0 || C > 128 || H <= 0 || W <= 0) return DRBA_E_ARG;
+    if (!x || !stats_zeroed || C <= 0 || C > 128 || C % 8 != 0 || H <= 0 || W <= 0) return DRBA_E_ARG;
+    if (!aligned16(x)) return DRBA_E_ALIGN;
     const size_t HW = (size_t)H * W;
-    const int ppb = 512;
+    int ppb = 512;
+    while (ppb > 64 && HW / ppb < 2 * kNumSMs) ppb >>= 1;     // enough blocks to fill the machine
     inorm_stats_kernel<<<cdiv(HW, ppb), kGfThreads, 0, as_stream(stream)>>>((const __half*)x, C, HW, ppb, stats_zeroed);
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
@@ -454,10 +510,11 @@ int drba_gmflow_inorm_stats(const void* x, int C, int H, int W, double* stats_ze
 int drba_gmflow_inorm_apply(const void* x, const double* stats, int relu_x, const void* skip, const double* skip_stats,
                             int final_relu, void* out, int C, int H, int W, void* stream)
 {
-    if (!x || !stats || !out || C <= 0 || H <= 0 || W <= 0) return DRBA_E_ARG;
-    const size_t n = (size_t)H * W * C;
+    if (!x || !stats || !out || C <= 0 || C % 8 != 0 || H <= 0 || W <= 0) return DRBA_E_ARG;
+    if (!aligned16(x) || !aligned16(out) || (skip && !aligned16(skip))) return DRBA_E_ALIGN;
+    const size_t n = (size_t)H * W * (C / 8);
     inorm_apply_kernel<<<cdiv(n, kGfThreads), kGfThreads, 0, as_stream(stream)>>>((const __half*)x, stats, relu_x, (const __half*)skip,
-                                                                                skip_stats, final_relu, (__half*)out, C, (size_t)H * W, nullptr, nullptr);
+                                                                                skip_stats, final_relu, (__half*)out, C, (size_t)H * W);
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
 }
@@ -486,8 +543,11 @@ int drba_gmflow_window_pack(const void* src, void* dst, int B, int h, int w, int
 int drba_gmflow_softmax_rows(void* S, int nwin_total, int Lw, int ld, int shifted, int k, int h, int w, void* stream)
 {
     if (!S || nwin_total <= 0 || Lw <= 0 || ld < Lw || k <= 0 || h % k != 0 || w % k != 0 || (h / k) * (w / k) != Lw) return DRBA_E_ARG;
-    const size_t threads = (size_t)nwin_total * Lw * 32;
-    softmax_rows_kernel<<<cdiv(threads, kGfThreads), kGfThreads, 0, as_stream(stream)>>>((__half*)S, nwin_total, Lw, ld, shifted, k, h / k, w / k, h, w);
+    if (ld > kSoftmaxMaxCols) return DRBA_E_UNSUPPORTED;
+    const dim3 grid(cdiv((size_t)Lw, kGfThreads / 32), nwin_total);
+    if (ld % 8 != 0 || !aligned16(S)) return DRBA_E_ALIGN;
+    if (ld <= 512) softmax_rows_kernel<2><<<grid, kGfThreads, 0, as_stream(stream)>>>((__half*)S, nwin_total, Lw, ld, shifted, k, h / k, w / k, h, w);
+    else softmax_rows_kernel<8><<<grid, kGfThreads, 0, as_stream(stream)>>>((__half*)S, nwin_total, Lw, ld, shifted, k, h / k, w / k, h, w);
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
 }

@@ -120,7 +120,13 @@ class GMFlow:
         return stream_ptr(self.device)
 
     def _chk(self, rc, what, n=1):
-        _lib.count(n)
+        """rc: the return code of an already issued call, or a zero-argument callable issuing it (then the call
+        is bracketed by the launch profiler's events under the family name `gmflow.<what>`)."""
+        if callable(rc):
+            with _lib.launch("gmflow." + what, n):
+                rc = rc()
+        else:
+            _lib.count(n)
         _lib.check(rc, what)
 
     def _pos_table(self, wh, ww):
@@ -146,10 +152,10 @@ class GMFlow:
         for k, x in enumerate(xs):
             s = self.buf(("st", tag, k, cch), (cch, 2), torch.float64)
             s.zero_()
-            self._chk(self.L.drba_gmflow_inorm_stats(ptr(x), cch, h, w, ptr(s), self.st()), "inorm_stats")
+            self._chk(lambda: self.L.drba_gmflow_inorm_stats(ptr(x), cch, h, w, ptr(s), self.st()), "inorm_stats")
             stats.append(s)
         for k, x in enumerate(xs):
-            self._chk(self.L.drba_gmflow_inorm_apply(ptr(x), ptr(stats[k]), relu_x, ptr(skips[k]) if skips else None,
+            self._chk(lambda: self.L.drba_gmflow_inorm_apply(ptr(x), ptr(stats[k]), relu_x, ptr(skips[k]) if skips else None,
                                                      ptr(skip_stats[k]) if skip_stats else None, final_relu, ptr(outs[k]), cch, h, w, self.st()),
                       "inorm_apply")
         return stats
@@ -159,7 +165,7 @@ class GMFlow:
         for k, x in enumerate(xs):
             s = self.buf(("st", tag, k, cch), (cch, 2), torch.float64)
             s.zero_()
-            self._chk(self.L.drba_gmflow_inorm_stats(ptr(x), cch, h, w, ptr(s), self.st()), "inorm_stats")
+            self._chk(lambda: self.L.drba_gmflow_inorm_stats(ptr(x), cch, h, w, ptr(s), self.st()), "inorm_stats")
             out.append(s)
         return out
 
@@ -171,12 +177,11 @@ class GMFlow:
         x = []
         for k, im in enumerate(imgs):
             nb = self.buf(("norm", k, H, W), (1, 3, H, W), torch.float32)
-            self._chk(self.L.drba_gmflow_normalize_img(ptr(im.float().contiguous()), ptr(nb), H, W, self.st()), "normalize")
+            self._chk(lambda: self.L.drba_gmflow_normalize_img(ptr(im.float().contiguous()), ptr(nb), H, W, self.st()), "normalize")
             raw = self.buf(("c1raw", k, H, W), (h1, w1, 64))
-            rc = self.L.drba_conv2d_direct_f32(ptr(nb), ptr(self.conv1_w), ptr(self.conv1_b), None, ptr(raw), 1, 1, 3, H, W,
-                                               _LL4(3 * H * W, H * W, W, 1), 64, h1, w1, _LL4(h1 * w1 * 64, 1, w1 * 64, 64),
-                                               2, 1, 0, 0, 49, self.conv1_dy, self.conv1_dx, 0, self.st())
-            self._chk(rc, "conv1 7x7")
+            self._chk(lambda: self.L.drba_conv2d_direct_f32(ptr(nb), ptr(self.conv1_w), ptr(self.conv1_b), None, ptr(raw), 1, 1, 3, H, W,
+                                                            _LL4(3 * H * W, H * W, W, 1), 64, h1, w1, _LL4(h1 * w1 * 64, 1, w1 * 64, 64),
+                                                            2, 1, 0, 0, 49, self.conv1_dy, self.conv1_dx, 0, self.st()), "conv1_7x7")
             x.append(raw)
         cur = [self.buf(("x0", k, H, W), (h1, w1, 64)) for k in range(2)]
         self._inorm(x, 64, h1, w1, cur, relu_x=1, tag="c1")
@@ -226,26 +231,26 @@ class GMFlow:
         qw = self.buf(("qw", h, w), (nw, Lw, C))
         kw = self.buf(("kw", h, w), (nw, Lp, C), zero=True)
         vt = self.buf(("vt", h, w), (nw, C, Lp), zero=True)
-        self._chk(L.drba_gmflow_window_pack(ptr(q), ptr(qw), 2, h, w, C, k, int(shifted), Lw, 0, self.st()), "window_pack")
-        self._chk(L.drba_gmflow_window_pack(ptr(kk), ptr(kw), 2, h, w, C, k, int(shifted), Lp, 0, self.st()), "window_pack")
-        self._chk(L.drba_gmflow_window_pack(ptr(v), ptr(vt), 2, h, w, C, k, int(shifted), Lp, 1, self.st()), "window_pack")
+        self._chk(lambda: L.drba_gmflow_window_pack(ptr(q), ptr(qw), 2, h, w, C, k, int(shifted), Lw, 0, self.st()), "window_pack")
+        self._chk(lambda: L.drba_gmflow_window_pack(ptr(kk), ptr(kw), 2, h, w, C, k, int(shifted), Lp, 0, self.st()), "window_pack")
+        self._chk(lambda: L.drba_gmflow_window_pack(ptr(v), ptr(vt), 2, h, w, C, k, int(shifted), Lp, 1, self.st()), "window_pack")
         S = self.buf(("S", h, w), (nw, Lw, Lp))
         run_program([Step(_Operand(kw, Lw, Lp, C), nw, Lw, [qw], [S], nw, Lw, Lp, act=ACT_NONE, bgemm=1)], self.device, tag="gmflow.qk")
-        self._chk(L.drba_gmflow_softmax_rows(ptr(S), nw, Lw, Lp, int(shifted), k, h, w, self.st()), "softmax_rows")
+        self._chk(lambda: L.drba_gmflow_softmax_rows(ptr(S), nw, Lw, Lp, int(shifted), k, h, w, self.st()), "softmax_rows")
         o = self.buf(("o", h, w), (nw, Lw, C))
         m = self.buf(("m", h, w), (nw, Lw, C))
         run_program([Step(_Operand(vt, C, C, Lp), nw, Lw, [S], [o], nw, Lw, C, act=ACT_NONE, bgemm=1),
                      Step(e["merge"], nw, Lw, [o], [m], nw, Lw, C, act=ACT_NONE)], self.device, tag="gmflow.pv")
         if not ffn:
-            self._chk(L.drba_gmflow_ln_residual(ptr(x), ptr(m), ptr(e["g1"]), ptr(e["b1"]), ptr(x), 2, h, w, C, k, int(shifted), Lw, 0, self.st()), "ln_residual")
+            self._chk(lambda: L.drba_gmflow_ln_residual(ptr(x), ptr(m), ptr(e["g1"]), ptr(e["b1"]), ptr(x), 2, h, w, C, k, int(shifted), Lw, 0, self.st()), "ln_residual")
             return
         cat = self.buf(("cat", h, w), (2, h, w, 2 * C))
-        self._chk(L.drba_gmflow_ln_residual(ptr(x), ptr(m), ptr(e["g1"]), ptr(e["b1"]), ptr(cat), 2, h, w, C, k, int(shifted), Lw, 1, self.st()), "ln_residual")
+        self._chk(lambda: L.drba_gmflow_ln_residual(ptr(x), ptr(m), ptr(e["g1"]), ptr(e["b1"]), ptr(cat), 2, h, w, C, k, int(shifted), Lw, 1, self.st()), "ln_residual")
         hid = self.buf(("hid", h, w), (2, h, w, 8 * C))
         m2 = self.buf(("m2", h, w), (2, h, w, C))
         run_program([Step(e["mlp0"], h, w, [cat[0], cat[1]], [hid[0], hid[1]], h, w, 8 * C, act=ACT_GELU),
                      Step(e["mlp2"], h, w, [hid[0], hid[1]], [m2[0], m2[1]], h, w, C, act=ACT_NONE)], self.device, tag="gmflow.ffn")
-        self._chk(L.drba_gmflow_ln_residual(ptr(x), ptr(m2), ptr(e["g2"]), ptr(e["b2"]), ptr(x), 2, h, w, C, 0, 0, 0, 0, self.st()), "ln_residual")
+        self._chk(lambda: L.drba_gmflow_ln_residual(ptr(x), ptr(m2), ptr(e["g2"]), ptr(e["b2"]), ptr(x), 2, h, w, C, 0, 0, 0, 0, self.st()), "ln_residual")
 
     # ---------------------------------------------------------------- forward
     def __call__(self, img0, img1):
@@ -268,10 +273,10 @@ class GMFlow:
                 if flow is not None:
                     up = resize_bilinear(flow, size=(h, w), align_corners=True)
                     flow = torch.empty_like(up)
-                    self._chk(L.drba_axpby_f32(ptr(up), 2.0, None, 0.0, ptr(flow), up.numel(), self.st()), "axpby")
-                    self._chk(L.drba_gmflow_warp_feature(ptr(feat[1]), ptr(flow), ptr(x[1]), h, w, C, self.st()), "warp_feature")
+                    self._chk(lambda: L.drba_axpby_f32(ptr(up), 2.0, None, 0.0, ptr(flow), up.numel(), self.st()), "axpby")
+                    self._chk(lambda: L.drba_gmflow_warp_feature(ptr(feat[1]), ptr(flow), ptr(x[1]), h, w, C, self.st()), "warp_feature")
                 pos = self._pos_table(h // k, w // k)
-                self._chk(L.drba_gmflow_add_position(ptr(x), ptr(pos), 2, h, w, h // k, w // k, C, self.st()), "add_position")
+                self._chk(lambda: L.drba_gmflow_add_position(ptr(x), ptr(pos), 2, h, w, h // k, w // k, C, self.st()), "add_position")
                 self.transformer_ref_order(x, h, w, k)
                 if dbg is not None:
                     dbg[f"tf{s}"] = x.clone()
@@ -281,14 +286,14 @@ class GMFlow:
                     S = self.buf(("corr", h, w), (1, n, _pad16(n)))
                     run_program([Step(_Operand(x[1].reshape(1, n, C), n, _pad16(n), C), 1, n, [x[0].reshape(1, n, C)], [S], 1, n, _pad16(n),
                                       act=ACT_NONE, bgemm=1)], dev, tag="gmflow.corr")
-                    self._chk(L.drba_gmflow_soft_readout(ptr(S), n, n, _pad16(n), None, w, 1, 1.0 / math.sqrt(C), ptr(pred), self.st()), "soft_readout")
+                    self._chk(lambda: L.drba_gmflow_soft_readout(ptr(S), n, n, _pad16(n), None, w, 1, 1.0 / math.sqrt(C), ptr(pred), self.st()), "soft_readout")
                 else:
-                    self._chk(L.drba_gmflow_local_match(ptr(x[0]), ptr(x[1]), h, w, C, radius, ptr(pred), self.st()), "local_match")
+                    self._chk(lambda: L.drba_gmflow_local_match(ptr(x[0]), ptr(x[1]), h, w, C, radius, ptr(pred), self.st()), "local_match")
                 if flow is None:
                     flow = pred
                 else:
                     tot = torch.empty_like(pred)
-                    self._chk(L.drba_axpby_f32(ptr(flow), 1.0, ptr(pred), 1.0, ptr(tot), pred.numel(), self.st()), "axpby")
+                    self._chk(lambda: L.drba_axpby_f32(ptr(flow), 1.0, ptr(pred), 1.0, ptr(tot), pred.numel(), self.st()), "axpby")
                     flow = tot
                 if dbg is not None:
                     dbg[f"match{s}"] = flow.clone()
@@ -303,24 +308,24 @@ class GMFlow:
                     run_program([Step(_Operand(kq.reshape(1, n, C), n, _pad16(n), C), 1, n, [q.reshape(1, n, C)], [S], 1, n, _pad16(n),
                                       act=ACT_NONE, bgemm=1)], dev, tag="gmflow.corr")
                     val = flow.reshape(2, n).t().contiguous()            # [n][2] value table (layout plumbing)
-                    self._chk(L.drba_gmflow_soft_readout(ptr(S), n, n, _pad16(n), ptr(val), w, 0, 1.0 / math.sqrt(C), ptr(out), self.st()), "soft_readout")
+                    self._chk(lambda: L.drba_gmflow_soft_readout(ptr(S), n, n, _pad16(n), ptr(val), w, 0, 1.0 / math.sqrt(C), ptr(out), self.st()), "soft_readout")
                 else:
                     run_program([Step(self.prop_q, h, w, [x[0]], [q], h, w, C, act=ACT_NONE),
                                  Step(self.prop_k, h, w, [x[0]], [kq], h, w, C, act=ACT_NONE)], dev, tag="gmflow.prop")
-                    self._chk(L.drba_gmflow_local_propagate(ptr(q), ptr(kq), ptr(flow), h, w, C, ptr(out), self.st()), "local_propagate")
+                    self._chk(lambda: L.drba_gmflow_local_propagate(ptr(q), ptr(kq), ptr(flow), h, w, C, ptr(out), self.st()), "local_propagate")
                 flow = out
                 if dbg is not None:
                     dbg[f"prop{s}"] = flow.clone()
             # convex upsampling x4 (gmflow.py:68-90)
             h, w = flow.shape[2], flow.shape[3]
             xin = self.buf(("upin", h, w), (h, w, 144))
-            self._chk(L.drba_gmflow_upsampler_input(ptr(flow), ptr(x[0]), ptr(xin), h, w, self.st()), "upsampler_input")
+            self._chk(lambda: L.drba_gmflow_upsampler_input(ptr(flow), ptr(x[0]), ptr(xin), h, w, self.st()), "upsampler_input")
             hid = self.buf(("uphid", h, w), (h, w, 256))
             mask = self.buf(("upmask", h, w), (h, w, 144))
             run_program([Step(self.up0, h, w, [xin], [hid], h, w, 256, act=ACT_RELU),
                          Step(self.up2, h, w, [hid], [mask], h, w, 144, act=ACT_NONE)], dev, tag="gmflow.upsampler")
             out = torch.empty((1, 2, 4 * h, 4 * w), dtype=torch.float32, device=dev)
-            self._chk(L.drba_gmflow_convex_upsample(ptr(mask), ptr(flow), ptr(out), h, w, self.st()), "convex_upsample")
+            self._chk(lambda: L.drba_gmflow_convex_upsample(ptr(mask), ptr(flow), ptr(out), h, w, self.st()), "convex_upsample")
         return out
 
     def transformer_ref_order(self, x, h, w, k):
@@ -353,20 +358,20 @@ class GMFlow:
         qw = self.buf(("qw", h, w), (nw, Lw, C))
         kw = self.buf(("kw", h, w), (nw, Lp, C), zero=True)
         vt = self.buf(("vt", h, w), (nw, C, Lp), zero=True)
-        self._chk(L.drba_gmflow_window_pack(ptr(q), ptr(qw), 2, h, w, C, k, int(shifted), Lw, 0, self.st()), "window_pack")
-        self._chk(L.drba_gmflow_window_pack(ptr(kk), ptr(kw), 2, h, w, C, k, int(shifted), Lp, 0, self.st()), "window_pack")
-        self._chk(L.drba_gmflow_window_pack(ptr(v), ptr(vt), 2, h, w, C, k, int(shifted), Lp, 1, self.st()), "window_pack")
+        self._chk(lambda: L.drba_gmflow_window_pack(ptr(q), ptr(qw), 2, h, w, C, k, int(shifted), Lw, 0, self.st()), "window_pack")
+        self._chk(lambda: L.drba_gmflow_window_pack(ptr(kk), ptr(kw), 2, h, w, C, k, int(shifted), Lp, 0, self.st()), "window_pack")
+        self._chk(lambda: L.drba_gmflow_window_pack(ptr(v), ptr(vt), 2, h, w, C, k, int(shifted), Lp, 1, self.st()), "window_pack")
         S = self.buf(("S", h, w), (nw, Lw, Lp))
         run_program([Step(_Operand(kw, Lw, Lp, C), nw, Lw, [qw], [S], nw, Lw, Lp, act=ACT_NONE, bgemm=1)], self.device, tag="gmflow.qk")
-        self._chk(L.drba_gmflow_softmax_rows(ptr(S), nw, Lw, Lp, int(shifted), k, h, w, self.st()), "softmax_rows")
+        self._chk(lambda: L.drba_gmflow_softmax_rows(ptr(S), nw, Lw, Lp, int(shifted), k, h, w, self.st()), "softmax_rows")
         o = self.buf(("o", h, w), (nw, Lw, C))
         m = self.buf(("m", h, w), (nw, Lw, C))
         run_program([Step(_Operand(vt, C, C, Lp), nw, Lw, [S], [o], nw, Lw, C, act=ACT_NONE, bgemm=1),
                      Step(e["merge"], nw, Lw, [o], [m], nw, Lw, C, act=ACT_NONE)], self.device, tag="gmflow.pv")
         cat = self.buf(("cat", h, w), (2, h, w, 2 * C))
-        self._chk(L.drba_gmflow_ln_residual(ptr(x), ptr(m), ptr(e["g1"]), ptr(e["b1"]), ptr(cat), 2, h, w, C, k, int(shifted), Lw, 1, self.st()), "ln_residual")
+        self._chk(lambda: L.drba_gmflow_ln_residual(ptr(x), ptr(m), ptr(e["g1"]), ptr(e["b1"]), ptr(cat), 2, h, w, C, k, int(shifted), Lw, 1, self.st()), "ln_residual")
         hid = self.buf(("hid", h, w), (2, h, w, 8 * C))
         m2 = self.buf(("m2", h, w), (2, h, w, C))
         run_program([Step(e["mlp0"], h, w, [cat[0], cat[1]], [hid[0], hid[1]], h, w, 8 * C, act=ACT_GELU),
                      Step(e["mlp2"], h, w, [hid[0], hid[1]], [m2[0], m2[1]], h, w, C, act=ACT_NONE)], self.device, tag="gmflow.ffn")
-        self._chk(L.drba_gmflow_ln_residual(ptr(x), ptr(m2), ptr(e["g2"]), ptr(e["b2"]), ptr(x), 2, h, w, C, 0, 0, 0, 0, self.st()), "ln_residual")
+        self._chk(lambda: L.drba_gmflow_ln_residual(ptr(x), ptr(m2), ptr(e["g2"]), ptr(e["b2"]), ptr(x), 2, h, w, C, 0, 0, 0, 0, self.st()), "ln_residual")

@@ -162,3 +162,19 @@ def find_gmfss_weights(explicit=None):
         if c and os.path.isfile(os.path.join(c, "fusionnet.pkl")):
             return c
     return None
+
+
+def load_gmflow_state(weights_dir):
+    raw = torch.load(os.path.join(weights_dir, "flownet.pkl"), map_location="cpu")
+    return {k: v.detach().float().contiguous() for k, v in raw.items()}
+
+
+def find_gmflow_weights(explicit=None):
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = [explicit, os.environ.get("DRBA_GMFSS_WEIGHTS"), "weights/train_log_gmfss",
+             os.path.join(here, "weights/train_log_gmfss"), os.path.join(here, "baseline/_ref/weights/train_log_gmfss"),
+             "/root/reference/weights/train_log_gmfss"]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "flownet.pkl")):
+            return c
+    return None

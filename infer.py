@@ -2,7 +2,7 @@
 """DRBA command line, re-hosted on the B200 implementation of the hot path.
 
 Same flags and loop semantics as the reference's infer.py (:18-36 flags, :58-174 loop); the
-per-window work runs in libdrba_b200.so.  Only `-m rife` is served by the CLI (GMFSS needs GMFlow, the missing row of
+per-window work runs in libdrba_b200.so.  `-m rife` and `-m gmfss` are served (gmfss_union is the open row of
 SURVEY.md 8 are next); other model names raise like the reference's unknown-model branch.
 Extra flags: --precision {fp16,fp32} (conv engine), --weights DIR.
 """
@@ -47,8 +47,15 @@ def load_model(model_type, scale, device, precision, weights):
         if wdir is None:
             raise FileNotFoundError('weights/train_log_rife_426_heavy/flownet.pkl')
         return RIFE(weights=wdir, scale=scale, device=device, precision=precision)
-    if model_type in ('gmfss', 'gmfss_union'):
-        raise NotImplementedError(f'{model_type}: GMFlow (SURVEY.md 8a-9) is not built yet; drba_b200.gmfss.GMFSS runs with an injected flow_estimator (see INTEGRATION.md 3b)')
+    if model_type == 'gmfss':
+        from drba_b200.gmfss import GMFSS
+        from drba_b200.weights import find_gmfss_weights
+        wdir = find_gmfss_weights(weights)
+        if wdir is None:
+            raise FileNotFoundError('weights/train_log_gmfss/fusionnet.pkl')
+        return GMFSS(weights=wdir, scale=scale, device=device)
+    if model_type == 'gmfss_union':
+        raise NotImplementedError('gmfss_union: not part of this build yet (SURVEY.md section 8: union Model and its IFNet variant)')
     raise ValueError(f'model_type must in {model_type}')
 
 

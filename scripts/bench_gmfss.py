@@ -36,12 +36,18 @@ def main():
     dev = torch.device("cuda", 0)
     w = find_gmfss_weights()
     state = load_gmfss_state(w) if w else synth_gmfss_state(0)
+    if "flownet" not in state:
+        from drba_b200.weights import find_gmflow_weights, load_gmflow_state
+        wf = find_gmflow_weights()
+        if wf:
+            state["flownet"] = load_gmflow_state(wf)
     H, W = bench.net_size(1080, 1920)
     frames = bench.synth_clip(3, H, W, 7, dev)
     g = torch.Generator(device="cpu").manual_seed(1)
     lo = 4.0 * torch.randn((1, 2, H // 32, W // 32), generator=g)
     flow = torch.nn.functional.interpolate(lo, size=(H // 2, W // 2), mode="bilinear", align_corners=False).to(dev)
     m = GMFSS(state=state, device=dev, flow_estimator=lambda a, b: flow)
+    out = {"weights": "trained" if w else "synthetic", "net_input": [H, W]}
     if "flownet" in state:
         from drba_b200.gmflow import GMFlow
         from drba_b200.ops import resize_bilinear as _rb
@@ -55,7 +61,6 @@ def main():
         out["gmflow_conv_breakdown_ms"] = {k: round(v["ms"], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         out["gmflow_engine_TFLOPs"] = round(sum(v["flops"] for v in conv) / sum(v["ms"] for v in conv) / 1e9, 1)
         out["gmflow_engine_GFLOP"] = round(sum(v["flops"] for v in conv) / 1e9, 1)
-    out = {"weights": "trained" if w else "synthetic", "net_input": [H, W]}
     out["featurenet_2frames_ms"] = round(timeit(lambda: m.model.feat_ext([frames[0], frames[1]])), 3)
     r = m.model.reuse(frames[1], frames[0], 1.0)
     from drba_b200.ops import resize_bilinear
