@@ -59,6 +59,9 @@ SIGNATURES = {
     "drba_gmflow_upsampler_input": (_I, [_P, _P, _P, _I, _I, _P]),
     "drba_gmflow_convex_upsample": (_I, [_P, _P, _P, _I, _I, _P]),
     "drba_axpby_f32": (_I, [_P, _F, _P, _F, _P, _Z, _P]),
+    "drba_gmfss_union_fix_timesteps": (_I, [_P, _P, _P, _P, _Z, _P]),
+    "drba_gmfss_union_swap_nhwc_f16": (_I, [_P, _I, _P, _P, _I, _I, _P]),
+    "drba_gmfss_union_swap_nchw_f32": (_I, [_P, _P, _I, _P, _P, _I, _I, _P]),
     "drba_conv2d_direct_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P,
                                     _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "drba_conv_tc_f16": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),

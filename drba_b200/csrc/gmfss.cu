@@ -46,7 +46,8 @@ unpack_kernel(const __half* __restrict__ in, int cstride, float* __restrict__ ou
     if (i >= HW) return;
     for (int c = 0; c < C; ++c) {
         float v = __half2float(in[i * cstride + c]);
-        if (do_clamp) v = fminf(fmaxf(v, lo), hi);
+        if (do_clamp == 1) v = fminf(fmaxf(v, lo), hi);
+        else if (do_clamp == 2) v = tanhf(v) * 10.0f;       // union MetricNet: Tanh() then * 10 (model_gmfss_union/MetricNet.py:41-42,63)
         out[(size_t)c * HW + i] = v;
     }
 }
@@ -146,6 +147,51 @@ scale_flow_kernel(const float* __restrict__ flow, const float* __restrict__ metr
     oflow[i] = fu; oflow[hw + i] = fv; ometric[i] = z;
 }
 
+
+// ---- GMFSS_union: timestep alignment and swap masks (models/model_gmfss_union/GMFSS.py:118-152) ----------------
+// t0w / t1w: the timestep maps forward-warped with their side's flow; g0 / g1: the warped ones-maps.  Holes of
+// either side (g < 0.999) set both timesteps to 1 (:121-126).
+__global__ void __launch_bounds__(kGmThreads)
+union_fix_timesteps_kernel(float* __restrict__ t0w, float* __restrict__ t1w, const float* __restrict__ g0, const float* __restrict__ g1, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * kGmThreads + threadIdx.x;
+    if (i >= n) return;
+    if (g0[i] < 0.999f || g1[i] < 0.999f) { t0w[i] = 1.0f; t1w[i] = 1.0f; }
+}
+
+// mask0 = t0 / t1 > 25 takes side 2's value into side 1, mask1 = t1 / t0 > 25 the other way (:129-152); both read
+// the values from before the swap.  NHWC concat buffer [hw][2C] = [side 1 | side 2].
+__global__ void __launch_bounds__(kGmThreads)
+union_swap_nhwc_kernel(__half* __restrict__ x, int C, const float* __restrict__ t0, const float* __restrict__ t1, size_t hw)
+{
+    const size_t i = (size_t)blockIdx.x * kGmThreads + threadIdx.x;
+    const int G = C / 8;
+    if (i >= hw * (size_t)G) return;
+    const size_t p = i / G;
+    const int g = (int)(i - p * G);
+    const bool m0 = t0[p] / t1[p] > 25.0f, m1 = t1[p] / t0[p] > 25.0f;
+    if (!m0 && !m1) return;
+    uint4* a = reinterpret_cast<uint4*>(x + p * 2 * C + g * 8);
+    uint4* b = reinterpret_cast<uint4*>(x + p * 2 * C + C + g * 8);
+    const uint4 va = *a, vb = *b;
+    if (m0) *a = vb;
+    if (m1) *b = va;
+}
+
+__global__ void __launch_bounds__(kGmThreads)
+union_swap_nchw_kernel(float* __restrict__ a, float* __restrict__ b, int C, const float* __restrict__ t0, const float* __restrict__ t1, size_t hw)
+{
+    const size_t p = (size_t)blockIdx.x * kGmThreads + threadIdx.x;
+    if (p >= hw) return;
+    const bool m0 = t0[p] / t1[p] > 25.0f, m1 = t1[p] / t0[p] > 25.0f;
+    if (!m0 && !m1) return;
+    for (int c = 0; c < C; ++c) {
+        const float va = a[(size_t)c * hw + p], vb = b[(size_t)c * hw + p];
+        if (m0) a[(size_t)c * hw + p] = vb;
+        if (m1) b[(size_t)c * hw + p] = va;
+    }
+}
+
 }  // namespace drba
 
 using namespace drba;
@@ -197,6 +243,34 @@ int drba_gmfss_scale_flow(const float* flow, const float* metric, const float* t
     if (H % s != 0 || W % s != 0) return DRBA_E_ARG;
     scale_flow_kernel<<<cdiv((size_t)(H / s) * (W / s), kGmThreads), kGmThreads, 0, as_stream(stream)>>>(
         flow, metric, tmap, tscalar, H, W, s, out_flow, out_metric);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+int drba_gmfss_union_fix_timesteps(float* t0w, float* t1w, const float* g0, const float* g1, size_t n, void* stream)
+{
+    if (!t0w || !t1w || !g0 || !g1) return DRBA_E_ARG;
+    if (n == 0) return DRBA_OK;
+    union_fix_timesteps_kernel<<<cdiv(n, kGmThreads), kGmThreads, 0, as_stream(stream)>>>(t0w, t1w, g0, g1, n);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+int drba_gmfss_union_swap_nhwc_f16(void* x, int C, const float* t0, const float* t1, int h, int w, void* stream)
+{
+    if (!x || !t0 || !t1 || C <= 0 || C % 8 != 0 || h <= 0 || w <= 0) return DRBA_E_ARG;
+    if (!aligned16(x)) return DRBA_E_ALIGN;
+    const size_t hw = (size_t)h * w;
+    union_swap_nhwc_kernel<<<cdiv(hw * (C / 8), kGmThreads), kGmThreads, 0, as_stream(stream)>>>((__half*)x, C, t0, t1, hw);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+int drba_gmfss_union_swap_nchw_f32(float* a, float* b, int C, const float* t0, const float* t1, int h, int w, void* stream)
+{
+    if (!a || !b || !t0 || !t1 || C <= 0 || h <= 0 || w <= 0) return DRBA_E_ARG;
+    const size_t hw = (size_t)h * w;
+    union_swap_nchw_kernel<<<cdiv(hw, kGmThreads), kGmThreads, 0, as_stream(stream)>>>(a, b, C, t0, t1, hw);
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
 }

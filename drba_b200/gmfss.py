@@ -39,12 +39,12 @@ def _splat_lists_build(flow, metric, h, w, device):
 
 
 class Model:
-    def __init__(self, state, device, flow_estimator=None):
+    def __init__(self, state, device, flow_estimator=None, union=False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.DrbaError("drba_b200 GMFSS runs on a CUDA device only; there is no CPU fallback")
         self.feat_ext = FeatureNet(state["feat"], self.device)
-        self.metricnet = MetricNet(state["metric"], self.device)
+        self.metricnet = MetricNet(state["metric"], self.device, union=union)
         self.fusionnet = GridNet(state["fusionnet"], self.device)
         if flow_estimator is None and "flownet" in state:
             from .gmflow import GMFlow
@@ -76,6 +76,12 @@ class Model:
 
     # models/model_gmfss/GMFSS.py:85-190
     def inference(self, img0, img1, reuse_things, timestep0, timestep1, swap_thresh=1):
+        return self._inference(img0, img1, reuse_things, timestep0, timestep1, None, False)
+
+    def _inference(self, img0, img1, reuse_things, timestep0, timestep1, rife, align_timesteps):
+        """Shared body of Model.inference (gmfss: GMFSS.py:85-190; union: model_gmfss_union/GMFSS.py:81-155).
+        rife: None (gmfss: GridNet sees img0, I1t, I2t, img1) or the RIFE frame [1,3,h,w] (union: I1t, rife, I2t).
+        align_timesteps: union's timestep warping / hole filling / ratio > 25 swaps (:118-152)."""
         require_cuda(img0, img1)
         flow01, flow10, metric0, metric1, feats0, feats1 = reuse_things
         dev = self.device
@@ -89,8 +95,9 @@ class Model:
         x1 = B.get(("in1", h, w), (h, w, 128))
         x2 = B.get(("in2", h, w), (h // 2, w // 2, 256))
         x3 = B.get(("in3", h, w), (h // 4, w // 4, 384))
-        warped = []
+        warped, tw, gaps = [], [], []
         with torch.cuda.device(dev):
+            ones = torch.ones((1, 1, h, w), dtype=torch.float32, device=dev) if align_timesteps else None
             for side, (img_h, flow, metric, feats, t) in enumerate(((img0h, flow01, metric0, feats0, timestep0),
                                                                      (img1h, flow10, metric1, feats1, timestep1))):
                 flow, metric = flow.float().contiguous(), metric.float().contiguous()
@@ -110,13 +117,36 @@ class Model:
                             rc = L.drba_splat_lists_apply_nchw_f32(lists.data_ptr(), ptr(img_h), ptr(It), 3, hs, ws_, 1, 0, stream_ptr(dev))
                         _lib.check(rc, "drba_splat_lists_apply_nchw_f32")
                         warped.append(It)
+                        if align_timesteps:     # union :118-124: the timestep map and a ones map ride the same lists
+                            tws, g = torch.empty_like(tmap), torch.empty_like(tmap)
+                            with _lib.launch("splat_apply_nchw", 2, nbytes=float(hs * ws_ * 2 * (8 + 40))):
+                                rc = L.drba_splat_lists_apply_nchw_f32(lists.data_ptr(), ptr(tmap), ptr(tws), 1, hs, ws_, 1, 0, stream_ptr(dev))
+                                rc = rc or L.drba_splat_lists_apply_nchw_f32(lists.data_ptr(), ptr(ones), ptr(g), 1, hs, ws_, 1, 0, stream_ptr(dev))
+                            _lib.check(rc, "drba_splat_lists_apply_nchw_f32")
+                            tw.append(tws)
+                            gaps.append(g)
                     with _lib.launch("splat_apply_nhwc", 1, nbytes=float(hs * ws_ * (4 * C + 40))):
                         rc = L.drba_splat_lists_apply_nhwc_f16(lists.data_ptr(), ptr(feat), C, C, ptr(xbuf), 2 * C, side * C, hs, ws_,
                                                                1, 0, 1, float(slope), stream_ptr(dev))
                     _lib.check(rc, "drba_splat_lists_apply_nhwc_f16")
                     _lib.check(L.drba_splat_lists_release(lists.data_ptr(), hs, ws_, stream_ptr(dev)), "drba_splat_lists_release")
-            x = pack_planes(list(img0h[0]) + list(warped[0][0]) + list(warped[1][0]) + list(img1h[0]),
-                            B.get(("in0", h, w), (h, w, 16)), prelu=sl[0])
+            if align_timesteps:
+                t0w, t1w = tw
+                with _lib.launch("gmfss_union_masks", 5):
+                    rc = L.drba_gmfss_union_fix_timesteps(ptr(t0w), ptr(t1w), ptr(gaps[0]), ptr(gaps[1]), t0w.numel(), stream_ptr(dev))
+                    rc = rc or L.drba_gmfss_union_swap_nchw_f32(ptr(warped[0]), ptr(warped[1]), 3, ptr(t0w), ptr(t1w), h, w, stream_ptr(dev))
+                    rc = rc or L.drba_gmfss_union_swap_nhwc_f16(ptr(x1), 64, ptr(t0w), ptr(t1w), h, w, stream_ptr(dev))
+                _lib.check(rc, "drba_gmfss_union_*")
+                for sc, xbuf, C in ((0.5, x2, 128), (0.25, x3, 192)):
+                    a, b = resize_bilinear(t0w, scale_factor=sc), resize_bilinear(t1w, scale_factor=sc)
+                    with _lib.launch("gmfss_union_masks", 1):
+                        rc = L.drba_gmfss_union_swap_nhwc_f16(ptr(xbuf), C, ptr(a), ptr(b), a.shape[2], a.shape[3], stream_ptr(dev))
+                    _lib.check(rc, "drba_gmfss_union_swap_nhwc_f16")
+            if rife is None:
+                planes = list(img0h[0]) + list(warped[0][0]) + list(warped[1][0]) + list(img1h[0])
+            else:
+                planes = list(warped[0][0]) + list(rife.float().contiguous()[0]) + list(warped[1][0])
+            x = pack_planes(planes, B.get(("in0", h, w), (h, w, 16)), prelu=sl[0])
             return self.fusionnet(x, x1, x2, x3)
 
 

@@ -66,13 +66,13 @@ def pack_planes(planes, out, prelu=None, scales=None):
     return out
 
 
-def unpack_planes(x, C, clamp=None):
-    """x [H][W][cstride] fp16 -> [1,C,H,W] fp32 (optionally clamped)."""
+def unpack_planes(x, C, clamp=None, tanh10=False):
+    """x [H][W][cstride] fp16 -> [1,C,H,W] fp32 (optionally clamped, or tanh(x) * 10)."""
     H, W, cs = x.shape
     out = torch.empty((1, C, H, W), dtype=torch.float32, device=x.device)
     lo, hi = clamp if clamp is not None else (0.0, 0.0)
     with _lib.launch("unpack_planes", 1, nbytes=float(H * W * (2 * cs + 4 * C))):
-        rc = _lib.lib().drba_unpack_nhwc_f16(ptr(x), cs, ptr(out), C, H, W, 0 if clamp is None else 1, float(lo), float(hi),
+        rc = _lib.lib().drba_unpack_nhwc_f16(ptr(x), cs, ptr(out), C, H, W, 2 if tanh10 else (0 if clamp is None else 1), float(lo), float(hi),
                                              stream_ptr(x.device))
     _lib.check(rc, "drba_unpack_nhwc_f16")
     return out
@@ -126,8 +126,9 @@ class MetricNet:
     """models/model_gmfss/MetricNet.py:23-65: (img0, img1, flow01, flow10) at half resolution -> metric0, metric1
     [1,1,h,w] fp32."""
 
-    def __init__(self, sd, device):
+    def __init__(self, sd, device, union=False):
         self.device = torch.device(device)
+        self.union = union      # model_gmfss_union/MetricNet.py:41-42,63: Tanh() on the output, then * 10
         d = self.device
         self.p = [_f(sd["metric_net1.0.weight"]), _f(sd["metric_net2.0.weight"]), _f(sd["metric_net3.0.weight"]),
                   _f(sd["metric_out.0.weight"])]
@@ -158,7 +159,7 @@ class MetricNet:
                      Step(L[3], h, w, [act[0]], [act[1]], h, w, 64, res=[raw[2]], act=ACT_PRELU, slope0=p[3]),
                      Step(L[4], h, w, [act[1]], [o16], h, w, 16, act=ACT_NONE)]
             run_program(steps, self.device, tag="metricnet")
-            m = unpack_planes(o16, 2)
+            m = unpack_planes(o16, 2, tanh10=self.union)
         return m[:, :1], m[:, 1:2]
 
 
@@ -183,7 +184,8 @@ class GridNet:
 
         self.blk = {}
         for name in ("head", "head1", "head2", "head3", "01", "04", "05", "11", "14", "15", "21", "24", "25"):
-            self.blk[name] = block("residual_model_" + name)
+            src = "head0" if (name == "head" and "residual_model_head0.0.weight" in sd) else name     # union names its image head `head0`
+            self.blk[name] = block("residual_model_" + src)
         for name in ("10", "20", "11", "21"):
             self.blk["d" + name] = block("downsample_model_" + name, stride=2)
         for name in ("04", "14", "05", "15"):

@@ -97,7 +97,8 @@ def _prelu_conv_pairs(prefix, cin, cout, transposed=False):
             (f"{prefix}.2.weight", (1,)), (f"{prefix}.3.weight", (cout, cout, 3, 3)), (f"{prefix}.3.bias", (cout,))]
 
 
-def gmfss_param_shapes():
+def gmfss_param_shapes(union=False):
+    """union=True: models/model_gmfss_union (image head `residual_model_head0` with 9 input channels)."""
     feat, metric, fusion = [], [], []
     for name, cin, c in (("block1", 3, 64), ("block2", 64, 128), ("block3", 128, 192)):
         feat += _prelu_conv_pairs(name, cin, c)
@@ -105,7 +106,7 @@ def gmfss_param_shapes():
     for i in (1, 2, 3):
         metric += [(f"metric_net{i}.0.weight", (1,)), (f"metric_net{i}.1.weight", (64, 64, 3, 3)), (f"metric_net{i}.1.bias", (64,))]
     metric += [("metric_out.0.weight", (1,)), ("metric_out.1.weight", (2, 64, 3, 3)), ("metric_out.1.bias", (2,))]
-    for name, cin, c in (("head", 12, 64), ("head1", 128, 64), ("head2", 256, 128), ("head3", 384, 192),
+    for name, cin, c in ((("head0", 9, 64) if union else ("head", 12, 64)), ("head1", 128, 64), ("head2", 256, 128), ("head3", 384, 192),
                          ("01", 64, 64), ("04", 64, 64), ("05", 64, 64), ("11", 128, 128), ("14", 128, 128), ("15", 128, 128),
                          ("21", 192, 192), ("24", 192, 192), ("25", 192, 192)):
         fusion += _prelu_conv_pairs("residual_model_" + name, cin, c)
@@ -120,12 +121,12 @@ def gmfss_param_shapes():
     return {"feat": feat, "metric": metric, "fusionnet": fusion}
 
 
-def synth_gmfss_state(seed=0):
+def synth_gmfss_state(seed=0, union=False):
     """Seeded stand-in weights of the GMFSS nets (same names / shapes as feat.pkl, metric.pkl, fusionnet.pkl)."""
     g = torch.Generator(device="cpu")
-    g.manual_seed(2000 + int(seed))
+    g.manual_seed(2000 + int(seed) + (500 if union else 0))
     out = {}
-    for net, shapes in gmfss_param_shapes().items():
+    for net, shapes in gmfss_param_shapes(union).items():
         sd = {}
         for name, shape in shapes:
             if shape == (1,):

@@ -244,6 +244,13 @@ DRBA_API int drba_gmfss_metric_prep(const float* img0, const float* img1, const 
                                     void* out_nhwc16, int H, int W, void* stream);
 DRBA_API int drba_gmfss_scale_flow(const float* flow, const float* metric, const float* tmap, float tscalar,
                                    int H, int W, int s, float* out_flow, float* out_metric, void* stream);
+/* GMFSS_union (models/model_gmfss_union/GMFSS.py:118-152): holes of either warped ones-map set both warped timestep
+ * maps to 1; then where t0/t1 > 25 side 1 takes side 2's values and where t1/t0 > 25 the other way round, on the
+ * NHWC fp16 concat buffer [h][w][2C] = [side 1 | side 2] or on two NCHW fp32 tensors.  drba_unpack_nhwc_f16 with
+ * do_clamp == 2 applies tanh(x) * 10 (union MetricNet head). */
+DRBA_API int drba_gmfss_union_fix_timesteps(float* t0w, float* t1w, const float* g0, const float* g1, size_t n, void* stream);
+DRBA_API int drba_gmfss_union_swap_nhwc_f16(void* x, int C, const float* t0, const float* t1, int h, int w, void* stream);
+DRBA_API int drba_gmfss_union_swap_nchw_f32(float* a, float* b, int C, const float* t0, const float* t1, int h, int w, void* stream);
 
 /* ---------------------------------------------------------------------------
  * GMFlow glue (csrc/gmflow.cu; models/gmflow/*).  Every dense contraction of GMFlow runs on

@@ -232,11 +232,73 @@ def gen_gmfss():
     print("gmfss_golden.npz:", len(out), "arrays")
 
 
+def gen_union():
+    """GMFSS_UNION (models/gmfss_union.py, models/model_gmfss_union/*) in fp32 on CPU: one DRBA window per weight set
+    (seeded synthetic GMFSS nets + synthetic RIFE, and the trained checkpoints), with the GMFlow flows stored."""
+    import torch.nn.functional as F
+    from models import gmfss_union as ref_union
+    from models.model_gmfss_union.GMFSS import Model
+    from models.rife_426_heavy.IFNet_HDv3 import IFNet
+    from drba_b200.gmfss_union import load_union_rife_state
+    from drba_b200.weights import load_gmfss_state, synth_gmfss_state, synth_ifnet_state
+
+    torch.set_grad_enabled(False)
+    g = torch.Generator().manual_seed(21)
+    H, W = 128, 256
+
+    def smooth(shape):
+        lo = torch.rand((shape[0], shape[1], shape[2] // 8 + 2, shape[3] // 8 + 2), generator=g)
+        hi = F.interpolate(lo, scale_factor=8, mode="bicubic", align_corners=False)[:, :, 4:4 + shape[2], 4:4 + shape[3]]
+        return (hi + 0.05 * torch.rand(shape, generator=g)).clamp(0, 1)
+
+    base = smooth((1, 3, H + 16, W + 16))
+    I0 = base[:, :, 8:8 + H, 8:8 + W].contiguous()
+    I1 = base[:, :, 7:7 + H, 10:10 + W].contiguous()
+    I2 = base[:, :, 5:5 + H, 13:13 + W].contiguous()
+    out = {"I0": I0.numpy(), "I1": I1.numpy(), "I2": I2.numpy()}
+    wdir = os.path.join(REF, "weights/train_log_gmfss_union")
+    for tag, state, rife_state in [("synth", synth_gmfss_state(0, union=True), synth_ifnet_state(0)),
+                                   ("real", load_gmfss_state(wdir), load_union_rife_state(wdir))]:
+        m = ref_union.GMFSS_UNION.__new__(ref_union.GMFSS_UNION)
+        m.model = Model()
+        _load = torch.load      # the union loader has no map_location (model_gmfss_union/GMFSS.py:50-53; SURVEY.md C.13)
+        torch.load = lambda f, *a, **k: _load(f, *a, **{**k, "map_location": "cpu"})
+        try:
+            m.model.load_model(wdir, -1)
+        finally:
+            torch.load = _load
+        m.model.feat_ext.load_state_dict(state["feat"], strict=True)
+        m.model.metricnet.load_state_dict(state["metric"], strict=True)
+        m.model.fusionnet.load_state_dict(state["fusionnet"], strict=True)
+        m.model.eval()
+        m.ifnet = IFNet().eval()
+        m.ifnet.load_state_dict(rife_state, strict=False)
+        m.scale = 1.0
+        m.scale_list = [16, 8, 4, 2, 1]
+        m.pad_size = 128
+        with torch.inference_mode():
+            if tag == "synth":
+                r10 = m.model.reuse(I1, I0, 1.0)
+                r12 = m.model.reuse(I1, I2, 1.0)
+                out["flow10"], out["flow01"] = r10[0].numpy(), r10[1].numpy()
+                out["flow12"], out["flow21"] = r12[0].numpy(), r12[1].numpy()
+            body = ref_union.GMFSS_UNION.inference_ts_drba.__wrapped__.__wrapped__
+            o1, reuse = body(m, I0, I1, I2, np.array([0.6, 1.0, 1.4]), None, True)
+            out[f"{tag}_w0_0.6"], out[f"{tag}_w0_1.4"] = o1[0].numpy().astype(np.float16), o1[2].numpy().astype(np.float16)
+            out[f"{tag}_metric12"] = reuse[3].numpy()      # reuse = (flow21, flow12, metric21, metric12, ...)
+            o2 = ref_union.GMFSS_UNION.inference_ts.__wrapped__.__wrapped__(m, I0, I1, [0.5])
+            out[f"{tag}_ts0.5"] = o2[0].numpy().astype(np.float16)
+    np.savez_compressed(os.path.join(HERE, "union_golden.npz"), **out)
+    print("union_golden.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "rife", "gmfss"]
+    which = sys.argv[1:] or ["ops", "rife", "gmfss", "union"]
     if "ops" in which:
         gen_ops()
     if "rife" in which:
         gen_rife()
     if "gmfss" in which:
         gen_gmfss()
+    if "union" in which:
+        gen_union()
