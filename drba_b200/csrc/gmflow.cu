@@ -230,6 +230,48 @@ softmax_rows_kernel(__half* __restrict__ S, int nwin_total, int Lw, int ld, int 
     }
 }
 
+// rows longer than 2048 columns (GMFlow inputs above 544x960 with 2 splits): three passes over the row
+constexpr int kSoftmaxGenericCols = 8192;
+__global__ void __launch_bounds__(kGfThreads)
+softmax_rows_generic_kernel(__half* __restrict__ S, int nwin_total, int Lw, int ld, int shifted, int k, int wh, int ww, int h, int w)
+{
+    __shared__ unsigned char region[kSoftmaxGenericCols];
+    const int win_b = blockIdx.y, win = win_b % (k * k);
+    const int sh = wh / 2, sw = ww / 2;
+    if (shifted) {
+        for (int j = threadIdx.x; j < Lw; j += kGfThreads) region[j] = (unsigned char)shift_region(j, win, k, wh, ww, h, w, sh, sw);
+        __syncthreads();
+    }
+    const int q = blockIdx.x * (kGfThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= Lw) return;
+    __half* row = S + ((size_t)win_b * Lw + q) * ld;
+    const int rq = shifted ? region[q] : 0;
+    float mx = -3.0e38f;
+    for (int j = lane; j < Lw; j += 32) {
+        float v = __half2float(row[j]);
+        if (shifted && region[j] != rq) v += -100.0f;
+        mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int j = lane; j < Lw; j += 32) {
+        float v = __half2float(row[j]);
+        if (shifted && region[j] != rq) v += -100.0f;
+        sum += __expf(v - mx);
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < ld; j += 32) {
+        float o = 0.0f;
+        if (j < Lw) {
+            float v = __half2float(row[j]);
+            if (shifted && region[j] != rq) v += -100.0f;
+            o = __expf(v - mx) * inv;
+        }
+        row[j] = __float2half_rn(o);
+    }
+}
+
 // ---- LayerNorm + residual (transformer.py:177-188) -----------------------------------------------------
 // m: [rows][C] fp16 in WINDOW order when k > 0 (rows = (b, win, l)), else token order.
 // out[token] = src[token] + LN(m[row(token)]) * gamma + beta        (cat == 0)
@@ -543,8 +585,13 @@ int drba_gmflow_window_pack(const void* src, void* dst, int B, int h, int w, int
 int drba_gmflow_softmax_rows(void* S, int nwin_total, int Lw, int ld, int shifted, int k, int h, int w, void* stream)
 {
     if (!S || nwin_total <= 0 || Lw <= 0 || ld < Lw || k <= 0 || h % k != 0 || w % k != 0 || (h / k) * (w / k) != Lw) return DRBA_E_ARG;
-    if (ld > kSoftmaxMaxCols) return DRBA_E_UNSUPPORTED;
+    if (ld > kSoftmaxGenericCols) return DRBA_E_UNSUPPORTED;
     const dim3 grid(cdiv((size_t)Lw, kGfThreads / 32), nwin_total);
+    if (ld > kSoftmaxMaxCols) {
+        softmax_rows_generic_kernel<<<grid, kGfThreads, 0, as_stream(stream)>>>((__half*)S, nwin_total, Lw, ld, shifted, k, h / k, w / k, h, w);
+        DRBA_RETURN_IF_LAUNCH_FAILED();
+        return DRBA_OK;
+    }
     if (ld % 8 != 0 || !aligned16(S)) return DRBA_E_ALIGN;
     if (ld <= 512) softmax_rows_kernel<2><<<grid, kGfThreads, 0, as_stream(stream)>>>((__half*)S, nwin_total, Lw, ld, shifted, k, h / k, w / k, h, w);
     else softmax_rows_kernel<8><<<grid, kGfThreads, 0, as_stream(stream)>>>((__half*)S, nwin_total, Lw, ld, shifted, k, h / k, w / k, h, w);

@@ -52,6 +52,13 @@ class Model:
         self.flow_estimator = flow_estimator
         self.version = 3.9
 
+    def _scaled(self, x, alpha):
+        out = torch.empty_like(x)
+        with _lib.launch("axpby", 1, nbytes=8.0 * x.numel()):
+            rc = _lib.lib().drba_axpby_f32(ptr(x), float(alpha), None, 0.0, ptr(out), x.numel(), stream_ptr(self.device))
+        _lib.check(rc, "drba_axpby_f32")
+        return out
+
     # models/model_gmfss/GMFSS.py:58-83
     def reuse(self, img0, img1, scale):
         require_cuda(img0, img1)
@@ -69,8 +76,8 @@ class Model:
         flow01 = self.flow_estimator(imgf0, imgf1)
         flow10 = self.flow_estimator(imgf1, imgf0)
         if scale != 1.0:
-            flow01 = resize_bilinear(flow01, scale_factor=1. / scale) / scale
-            flow10 = resize_bilinear(flow10, scale_factor=1. / scale) / scale
+            flow01 = self._scaled(resize_bilinear(flow01, scale_factor=1. / scale), 1. / scale)
+            flow10 = self._scaled(resize_bilinear(flow10, scale_factor=1. / scale), 1. / scale)
         metric0, metric1 = self.metricnet(img0h, img1h, flow01, flow10)
         return flow01, flow10, metric0, metric1, feat_ext0, feat_ext1
 

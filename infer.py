@@ -2,8 +2,8 @@
 """DRBA command line, re-hosted on the B200 implementation of the hot path.
 
 Same flags and loop semantics as the reference's infer.py (:18-36 flags, :58-174 loop); the
-per-window work runs in libdrba_b200.so.  `-m rife` and `-m gmfss` are served (gmfss_union is the open row of
-SURVEY.md 8 are next); other model names raise like the reference's unknown-model branch.
+per-window work runs in libdrba_b200.so.  `-m rife`, `-m gmfss` and `-m gmfss_union` are served; other model
+names raise like the reference's unknown-model branch.
 Extra flags: --precision {fp16,fp32} (conv engine), --weights DIR.
 """
 import argparse
@@ -55,7 +55,13 @@ def load_model(model_type, scale, device, precision, weights):
             raise FileNotFoundError('weights/train_log_gmfss/fusionnet.pkl')
         return GMFSS(weights=wdir, scale=scale, device=device)
     if model_type == 'gmfss_union':
-        raise NotImplementedError('gmfss_union: not part of this build yet (SURVEY.md section 8: union Model and its IFNet variant)')
+        from drba_b200.gmfss_union import GMFSS_UNION
+        wdir = weights or 'weights/train_log_gmfss_union'
+        for cand in (wdir, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'baseline/_ref/weights/train_log_gmfss_union'),
+                     '/root/reference/weights/train_log_gmfss_union'):
+            if os.path.isfile(os.path.join(cand, 'fusionnet.pkl')):
+                return GMFSS_UNION(weights=cand, scale=scale, device=device, precision=precision)
+        raise FileNotFoundError('weights/train_log_gmfss_union/fusionnet.pkl')
     raise ValueError(f'model_type must in {model_type}')
 
 
