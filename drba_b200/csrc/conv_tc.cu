@@ -73,6 +73,10 @@ struct alignas(64) LayerDev {
     int resident;           // 1: weights resident in smem for the whole layer
     int bgemm;              // 1: batched GEMM: the weight rows of a tile are those of batch element oy0 (H = batch)
     int has_bias;
+    int halo;               // 1: 3x3 stride-1 layer whose taps are descriptor offsets into ONE halo tile per K chunk
+    int nst;                // ring stages used by this layer
+    int a_base, a_stride;   // byte offset of the activation ring and bytes per stage
+    int halo_bo;            // experiment: write the descriptor's base_offset field
     int ntile, nsplits, cout_pad, cout;
     int swz_bytes;          // 32 / 64 / 128
     int b_sub;              // bytes of one weight tile (padded to the swizzle period)
@@ -258,7 +262,9 @@ conv_tc_kernel(const __grid_constant__ Program prog)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) TC_TRACE(4091);
 
-    uint32_t stage = 0, phase = 0;   // smem ring position (both producers and the MMA warp keep their own copy)
+    // ring bookkeeping (both producers and the MMA warp keep identical copies): every layer starts at stage 0 and
+    // walks its own number of stages; bit s of `pbits` is the parity of the next `full` phase of stage s
+    uint32_t stage = 0, pbits = 0;
     uint32_t tcount = 0;             // tiles this CTA has started so far (MMA warp and epilogue warps keep their own copy)
     uint32_t bres_phase = 0;         // MMA warp: parity of the next resident-weights barrier phase
 
@@ -268,12 +274,14 @@ conv_tc_kernel(const __grid_constant__ Program prog)
         const int total_tiles = L.total_tiles, mtiles = L.mtiles, nsplits = L.nsplits, G = L.G;
         const int tiles_x = L.tiles_x, tile_w = L.tile_w, tile_h = L.tile_h, MT = L.MT;
         const int KI = L.KI, T = L.T, ntile = L.ntile, kchunks = L.kchunks, Kc = L.Kc, resident = L.resident;
-        const uint32_t a_base = resident ? smem + kBRegion : smem;
-        const uint32_t a_stride = resident ? kABytesMax : kStageBytes;
+        const uint32_t a_base = smem + (uint32_t)L.a_base;
+        const uint32_t a_stride = (uint32_t)L.a_stride;
+        const int nst = L.nst, halo = L.halo;
+        stage = 0;
 
         if (warp == 0) {
             // ===== activation producer: the whole warp walks the loop, one elected lane issues =====
-            const uint32_t a_bytes = (dbg & 2) ? 0u : (uint32_t)(MT * kTileM * Kc * 2);
+            const uint32_t a_bytes = (dbg & 2) ? 0u : (uint32_t)(halo ? (16 * MT + 2) * 16 * Kc * 2 : MT * kTileM * Kc * 2);
             if (li + 1 < nlayers && elect_one()) {
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].ta[0]) : "memory");
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].tb) : "memory");
@@ -289,18 +297,24 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 int tap = 0, kc = 0;
                 for (int it = 0; it < KI; ++it) {
                     if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 0);
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_wait(&empty_bar[stage], ((pbits >> stage) & 1u) ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(&full_bar[stage], a_bytes);
                         if (resident) mbar_arrive(&full_bar[stage]);      // stands in for the weight producer
-                        const int e = L.tapc[g][tap];
-                        const int cy = (e & 0xff) - 64, cx = ((e >> 8) & 0xff) - 64, pary = (e >> 16) & 1, parx = (e >> 17) & 1;
-                        if (!(dbg & 2)) tma_load_5d(a_base + stage * a_stride, ta, &full_bar[stage], kc * Kc, parx, ox0 + cx, pary, oy0 + cy);
+                        if (halo) {
+                            // one box per K chunk: the (16*MT+2) x 16 pixel neighbourhood of the 8 x 16*MT tile
+                            if (!(dbg & 2)) tma_load_5d(a_base + stage * a_stride, ta, &full_bar[stage], it * Kc, 0, ox0 - 1, 0, oy0 - 1);
+                        } else {
+                            const int e = L.tapc[g][tap];
+                            const int cy = (e & 0xff) - 64, cx = ((e >> 8) & 0xff) - 64, pary = (e >> 16) & 1, parx = (e >> 17) & 1;
+                            if (!(dbg & 2)) tma_load_5d(a_base + stage * a_stride, ta, &full_bar[stage], kc * Kc, parx, ox0 + cx, pary, oy0 + cy);
+                        }
                     }
                     __syncwarp();
                     if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 1);
                     if (++kc == kchunks) { kc = 0; ++tap; }
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    pbits ^= 1u << stage;
+                    if (++stage == (uint32_t)nst) stage = 0;
                 }
             }
         } else if (warp == 10) {
@@ -317,23 +331,25 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                     if (L.bgemm) brow0 += ((idx % mtiles) / tiles_x) * tile_h * MT * cout_pad;    // batch element = output row
                     int tap = 0, kc = 0;
                     for (int it = 0; it < KI; ++it) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        mbar_wait(&empty_bar[stage], ((pbits >> stage) & 1u) ^ 1u);
                         if (elect_one()) {
                             mbar_expect_tx(&full_bar[stage], b_bytes);
                             if (!(dbg & 4)) tma_load_2d(smem + stage * kStageBytes + kABytesMax, tb, &full_bar[stage], kc * Kc, brow0 + tap * cout_pad);
                         }
                         __syncwarp();
                         if (++kc == kchunks) { kc = 0; ++tap; }
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        pbits ^= 1u << stage;
+                        if (++stage == (uint32_t)nst) stage = 0;
                     }
                 }
             } else {
                 // keep the ring position in step with the other warps
                 const int mine = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-                const uint32_t adv = (uint32_t)mine * (uint32_t)KI;
-                const uint32_t pos = stage + adv;
-                phase ^= (pos / kStages) & 1u;
-                stage = pos % kStages;
+                const uint32_t uses = (uint32_t)mine * (uint32_t)KI;     // stage s is used ceil((uses - s) / nst) times
+                for (uint32_t s2 = 0; s2 < (uint32_t)nst; ++s2) {
+                    const uint32_t cnt = uses > s2 ? (uses - s2 + nst - 1) / nst : 0u;
+                    pbits ^= (cnt & 1u) << s2;
+                }
             }
         } else if (warp == 1) {
             // ===== MMA issuer: whole warp in the loop, one elected lane issues =====
@@ -344,6 +360,10 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             const uint32_t a_mt16 = (uint32_t)(kTileM * Kc * 2) >> 4;     // one M tile inside the stage
             const uint32_t b_sub16 = (uint32_t)L.b_sub >> 4;
             const uint64_t desc_hi = make_desc(0, L.swz_bytes);
+            // halo mode: rows of an 8-pixel tile row are contiguous, tile rows are 16 pixels apart in the halo tile
+            const uint32_t rowb16 = (uint32_t)(Kc * 2) >> 4;
+            const uint64_t desc_hi_halo = (desc_hi & ~(0x3FFFull << 32)) | ((uint64_t)(16u * rowb16) << 32);
+            const int halo_bo = L.halo_bo;
             const uint32_t a_base16 = (a_base & 0x3FFFFu) >> 4, a_stride16 = a_stride >> 4;
             const uint32_t b_res16 = (smem & 0x3FFFFu) >> 4;
             if (resident && total_tiles > (int)blockIdx.x) {
@@ -356,32 +376,51 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 int r = idx / mtiles;
                 const int nsplit = r % nsplits; r /= nsplits;
                 const int g = r % G;
-                const uint32_t b_tile16 = b_res16 + (uint32_t)((g * nsplits + nsplit) * KI) * b_sub16;   // resident: tiles of (g, nsplit)
+                const uint32_t b_tile16 = b_res16 + (uint32_t)((g * nsplits + nsplit) * T * kchunks) * b_sub16;   // resident: tiles of (g, nsplit)
                 mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);     // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * (uint32_t)kMaxNTile;
                 uint32_t accumulate = 0;
                 for (int it = 0; it < KI; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait(&full_bar[stage], (pbits >> stage) & 1u);
                     tc_fence_after();
                     if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 2);
                     const uint32_t sa16 = a_base16 + stage * a_stride16;
-                    const uint32_t sb16 = resident ? b_tile16 + (uint32_t)it * b_sub16 : sa16 + (kABytesMax >> 4);
-                    if (elect_one()) {
-                        const uint64_t db = desc_hi | (uint64_t)sb16;
-                        for (int mt = 0; mt < MT; ++mt) {
-                            const uint64_t da = desc_hi | (uint64_t)(sa16 + mt * a_mt16);
-                            for (int k = 0; k < ksteps; ++k) {
-                                // advance 16 fp16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
-                                tc_mma_f16(tmem_d + mt * ntile + ((dbg & 8) ? (k & 1) * 64 : 0) + ((dbg & 16) ? (k & 3) * 32 : 0), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
+                    if (halo) {
+                        if (elect_one()) {
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int e = L.tapc[0][tap];
+                                const int dy = (e & 0xff) - 64, dx = ((e >> 8) & 0xff) - 64;
+                                const uint64_t db = desc_hi | (uint64_t)(b_tile16 + (uint32_t)(tap * kchunks + it) * b_sub16);
+                                for (int mt = 0; mt < MT; ++mt) {
+                                    const uint32_t start16 = sa16 + (uint32_t)((mt * 16 + dy + 1) * 16 + dx + 1) * rowb16;
+                                    uint64_t da = desc_hi_halo | (uint64_t)start16;
+                                    if (halo_bo) da |= (uint64_t)((start16 >> 3) & 7u) << 49;
+                                    for (int k = 0; k < ksteps; ++k)
+                                        tc_mma_f16(tmem_d + mt * ntile, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)(tap | k));
+                                }
                             }
+                            tc_commit(&empty_bar[stage]);
                         }
-                        tc_commit(&empty_bar[stage]);
+                    } else {
+                        const uint32_t sb16 = resident ? b_tile16 + (uint32_t)it * b_sub16 : sa16 + (kABytesMax >> 4);
+                        if (elect_one()) {
+                            const uint64_t db = desc_hi | (uint64_t)sb16;
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const uint64_t da = desc_hi | (uint64_t)(sa16 + mt * a_mt16);
+                                for (int k = 0; k < ksteps; ++k) {
+                                    // advance 16 fp16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
+                                    tc_mma_f16(tmem_d + mt * ntile, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
+                                }
+                            }
+                            tc_commit(&empty_bar[stage]);
+                        }
                     }
                     __syncwarp();
                     accumulate = 1;
                     if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 3);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    pbits ^= 1u << stage;
+                    if (++stage == (uint32_t)nst) stage = 0;
                 }
                 if (elect_one()) tc_commit(&acc_full[buf]);
                 __syncwarp();
@@ -434,13 +473,14 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                         __half* out = reinterpret_cast<__half*>(L.out[img]) + pix * cstride + nbase;
                         __half* out1 = L.out1[img] ? reinterpret_cast<__half*>(L.out1[img]) + pix * cstride + nbase : nullptr;
                         __half* out2 = L.out2[img] ? reinterpret_cast<__half*>(L.out2[img]) + pix * cstride + nbase : nullptr;
-                        const __half* res = (resb && valid) ? resb + pix * cstride + nbase : nullptr;
+                        const __half* res = (resb && valid && !(dbg & 16)) ? resb + pix * cstride + nbase : nullptr;
                         const __half* res2 = (L.res2[img] && valid) ? L.res2[img] + pix * cstride + nbase : nullptr;
                         for (int c0 = 0; c0 < ntile; c0 += 32) {
                             uint32_t rr[32];
                             tc_ld16_nowait(taddr + c0, rr);
                             if (c0 + 16 < ntile) tc_ld16_nowait(taddr + c0 + 16, rr + 16);
                             tc_ld_wait();
+                            if (idx == blockIdx.x && q == 2 && lane == 0 && mt == 0) TC_TRACE(li * 256 + 204 + (c0 >> 5) * 2);
                             if (!valid) continue;
 #pragma unroll
                             for (int hh = 0; hh < 2; ++hh) {
@@ -507,9 +547,10 @@ conv_tc_kernel(const __grid_constant__ Program prog)
 #pragma unroll
                                     for (int k = 0; k < 8; ++k) oh[k] = __floats2half2_rn(w[2 * k], w[2 * k + 1]);
                                     uint4* o4 = reinterpret_cast<uint4*>(op + c);
-                                    o4[0] = o[0]; o4[1] = o[1];
+                                    if (!(dbg & 8)) { o4[0] = o[0]; o4[1] = o[1]; }
                                 }
                             }
+                            if (idx == blockIdx.x && q == 2 && lane == 0 && mt == 0) TC_TRACE(li * 256 + 205 + (c0 >> 5) * 2);
                         }
                     } else {
                         // lastconv: group g = phase (py, px); channel co = c13*4 + i*2 + j lands at
@@ -650,24 +691,45 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     for (int cand = d.cout_pad < kMaxNTile ? d.cout_pad : kMaxNTile; cand >= 16; cand -= 16)
         if (d.cout_pad % cand == 0) { ntile = cand; break; }
     if (!ntile) return DRBA_E_UNSUPPORTED;
-    // M tiles per super tile: thin K steps stack M tiles so that one TMA box still carries 16 KB
+    const int b_bytes_pre = kMaxNTile * L.Kc * 2;
+    (void)b_bytes_pre;
+    // halo mode: a 3x3 stride-1 layer loads ONE (16*MT+2) x 16 pixel neighbourhood per K chunk and runs the nine
+    // taps as descriptor offsets into it (8-pixel-wide tiles keep every 8-row core group contiguous; the 16-pixel
+    // pitch keeps the swizzle phase identical for all groups) -- 4x fewer activation bytes than one box per tap.
+    // Needs the weights resident (checked below once ntile is final).
+    static int env_halo = -1, env_halo_bo = -1;
+    if (env_halo < 0) {
+        const char* e = getenv("DRBA_TC_HALO"); env_halo = e ? atoi(e) : 1;
+        e = getenv("DRBA_TC_HALO_BO"); env_halo_bo = e ? atoi(e) : 0;
+    }
+    bool halo = env_halo && S == 1 && T == 9 && G == 1 && d.epilogue == 0 && !d.bgemm;
+    if (halo)
+        for (int t = 0; t < 9; ++t)
+            if (d.dy[t] != t / 3 - 1 || d.dx[t] != t % 3 - 1) halo = false;
+    // M tiles per super tile: thin K steps stack M tiles so that one TMA box still carries ~16 KB
     int MT = kABytesMax / (kTileM * L.Kc * 2);
     while (MT > 1 && MT * ntile > kMaxNTile) MT >>= 1;
-    // pixel patch of an M tile: the rectangle whose super tiles cover the output with the least waste
     long best = -1;
-    const int shapes[5][2] = {{16, 8}, {32, 4}, {8, 16}, {64, 2}, {128, 1}};
     int best_mt = 1;
     L.tile_w = 16; L.tile_h = 8;
-    for (int mt = MT; mt >= 1; mt >>= 1) {
-        for (int i = 0; i < 5; ++i) {
-            const int sh = shapes[i][1] * mt;
-            if (sh > 256) continue;
-            if (d.bgemm && sh != 1) continue;      // a tile must not straddle batch elements
-            const long nt = (long)((OW + shapes[i][0] - 1) / shapes[i][0]) * ((OH + sh - 1) / sh);
-            const long cost = nt * mt;       // covered M tiles (waste included)
-            // prefer the larger super tile unless it wastes > 6 % more coverage
-            if (best < 0 || cost * 100 < best * 94 || (mt == best_mt && cost < best)) {
-                best = cost; best_mt = mt; L.tile_w = shapes[i][0]; L.tile_h = shapes[i][1];
+    if (halo) {
+        L.tile_w = 8; L.tile_h = 16;
+        while (MT > 1 && (OH + 16 * MT - 1) / (16 * MT) * MT * 100 > ((OH + 15) / 16) * 106) MT >>= 1;   // avoid > 6 % more rows
+        best_mt = MT;
+    } else {
+        // pixel patch of an M tile: the rectangle whose super tiles cover the output with the least waste
+        const int shapes[5][2] = {{16, 8}, {32, 4}, {8, 16}, {64, 2}, {128, 1}};
+        for (int mt = MT; mt >= 1; mt >>= 1) {
+            for (int i = 0; i < 5; ++i) {
+                const int sh = shapes[i][1] * mt;
+                if (sh > 256) continue;
+                if (d.bgemm && sh != 1) continue;      // a tile must not straddle batch elements
+                const long nt = (long)((OW + shapes[i][0] - 1) / shapes[i][0]) * ((OH + sh - 1) / sh);
+                const long cost = nt * mt;       // covered M tiles (waste included)
+                // prefer the larger super tile unless it wastes > 6 % more coverage
+                if (best < 0 || cost * 100 < best * 94 || (mt == best_mt && cost < best)) {
+                    best = cost; best_mt = mt; L.tile_w = shapes[i][0]; L.tile_h = shapes[i][1];
+                }
             }
         }
     }
@@ -694,22 +756,50 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     const int b_bytes = ntile * L.Kc * 2;
     const int swz_period = 8 * L.swz_bytes;
     L.b_sub = (b_bytes + swz_period - 1) / swz_period * swz_period;
-    L.KI = T * L.kchunks;
-    // weights resident in shared memory when every tile of the layer fits
-    L.resident = (!d.bgemm && (long)G * L.nsplits * L.KI * L.b_sub <= (long)kBRegion) ? 1 : 0;
-    {
-        static int env_res = -1;
-        if (env_res < 0) { const char* e = getenv("DRBA_TC_RESIDENT"); env_res = e ? atoi(e) : 1; }
-        if (!env_res) L.resident = 0;
-    }
     if (L.b_sub > kStageBytes - kABytesMax) return DRBA_E_UNSUPPORTED;
+    // shared-memory plan.  Resident mode: [all weight tiles of the layer | activation ring]; streaming mode: six
+    // stages of [A 16 KB | B 16 KB].  Halo mode needs resident weights.
+    const long total_smem = (long)kStages * kStageBytes;
+    const long w_bytes = ((long)G * L.nsplits * T * L.kchunks * L.b_sub + 1023) / 1024 * 1024;
+    const long a_stage = halo ? (((long)(16 * MT + 2) * 16 * L.Kc * 2 + 1023) / 1024 * 1024) : kABytesMax;
+    static int env_res = -1;
+    if (env_res < 0) { const char* e = getenv("DRBA_TC_RESIDENT"); env_res = e ? atoi(e) : 1; }
+    bool resident = env_res && !d.bgemm && w_bytes + 2 * a_stage <= total_smem && w_bytes <= (long)kBRegion + 32768;
+    if (halo && !resident) {
+        // fall back to one box per tap: redo the tile choice without the halo constraint
+        drba_conv_layer d2 = d;
+        (void)d2;
+        halo = false;
+        static thread_local int depth = 0;
+        if (depth == 0) {
+            ++depth;
+            const int saved = env_halo;
+            env_halo = 0;
+            const int rc = build_layer(d, nimg, L, encode);
+            env_halo = saved;
+            --depth;
+            return rc;
+        }
+    }
+    L.resident = resident ? 1 : 0;
+    L.halo = halo ? 1 : 0;
+    L.halo_bo = env_halo_bo;
+    L.KI = halo ? L.kchunks : T * L.kchunks;
+    if (resident) {
+        L.a_base = (int)w_bytes;
+        L.a_stride = (int)a_stage;
+        long nst = (total_smem - w_bytes) / a_stage;
+        L.nst = (int)(nst > kStages ? kStages : nst);
+    } else {
+        L.a_base = 0; L.a_stride = kStageBytes; L.nst = kStages;
+    }
 
     // A: input viewed as [H/S][S][W/S][S][C], innermost first
     for (int i = 0; i < nimg; ++i) {
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)S, (cuuint64_t)(W / S), (cuuint64_t)S, (cuuint64_t)(H / S)};
         const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)S * Cin * 2, (cuuint64_t)W * Cin * 2,
                                        (cuuint64_t)S * W * Cin * 2};
-        const cuuint32_t box[5] = {(cuuint32_t)L.Kc, 1, (cuuint32_t)L.tile_w, 1, (cuuint32_t)(L.tile_h * L.MT)};
+        const cuuint32_t box[5] = {(cuuint32_t)L.Kc, 1, (cuuint32_t)(L.halo ? 16 : L.tile_w), 1, (cuuint32_t)(L.halo ? 16 * L.MT + 2 : L.tile_h * L.MT)};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         const CUresult r = encode(&L.ta[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d.in[i]), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(L.swz_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -20,6 +20,8 @@ LAYERS = [  # name, cin, cout, h, w, stride, res
     ("block4.conv0a", 64, 16, 1088, 1920, 2, False),
     ("block4.conv0b", 16, 32, 544, 960, 2, False),
     ("encode.cnn1", 16, 16, 544, 960, 1, False),
+    ("gridnet64", 64, 64, 544, 960, 1, True),
+    ("gridnet128", 128, 128, 272, 480, 1, True),
 ]
 
 

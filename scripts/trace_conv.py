@@ -15,7 +15,8 @@ def main():
     from drba_b200.weights import synth_ifnet_state
     eng = IFNetEngine(synth_ifnet_state(0), "cuda", "fp32")
     cases = {"block0.res": (192, 192, 17, 30, 1, True), "block4.res": (32, 32, 272, 480, 1, True),
-             "block4.conv0a": (64, 16, 1088, 1920, 2, False), "block2.res": (96, 96, 68, 120, 1, True)}
+             "block4.conv0a": (64, 16, 1088, 1920, 2, False), "block2.res": (96, 96, 68, 120, 1, True),
+             "block3.res": (64, 64, 136, 240, 1, True), "gridnet64": (64, 64, 544, 960, 1, True)}
     names = sys.argv[1:] or list(cases)
     trace = torch.zeros(4096, dtype=torch.int64, device="cuda")
     for name in names:
@@ -53,6 +54,7 @@ def main():
             for r in rows:
                 print("   ", r)
             print(f"   epi: acc_full {rel(t[base + 200])} stores_done {rel(t[base + 201])} barrier_in {rel(t[base + 202])} barrier_out {rel(t[base + 203])}")
+            print(f"   epi detail (ld0 done, chunk0 stored, ld1 done, chunk1 stored): {[rel(t[base + 204 + i]) for i in range(4)]}")
 
 
 if __name__ == "__main__":
