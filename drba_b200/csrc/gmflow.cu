@@ -57,17 +57,17 @@ inorm_stats_kernel(const __half* __restrict__ x, int C, size_t HW, int pix_per_b
                 s[2 * j] += f.x; ss[2 * j] += f.x * f.x; s[2 * j + 1] += f.y; ss[2 * j + 1] += f.y * f.y;
             }
         }
-    __shared__ float sh[2][128];
-    for (int i = threadIdx.x; i < 2 * 128; i += kGfThreads) (&sh[0][0])[i] = 0.0f;
-    __syncthreads();
-    if (r < R) {
+    // fixed-order reduction over the R pixel lanes (deterministic); blocks meet in double precision, where the
+    // order of the atomics is far below fp32 resolution
+    __shared__ float sh[2][kGfThreads * 8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { atomicAdd(&sh[0][g * 8 + j], s[j]); atomicAdd(&sh[1][g * 8 + j], ss[j]); }
-    }
+    for (int j = 0; j < 8; ++j) { sh[0][(r * G + g) * 8 + j] = s[j]; sh[1][(r * G + g) * 8 + j] = ss[j]; }
     __syncthreads();
     if (threadIdx.x < C) {
-        atomicAdd(stats + 2 * threadIdx.x, (double)sh[0][threadIdx.x]);
-        atomicAdd(stats + 2 * threadIdx.x + 1, (double)sh[1][threadIdx.x]);
+        float a = 0.0f, b = 0.0f;
+        for (int k = 0; k < R; ++k) { a += sh[0][k * C + threadIdx.x]; b += sh[1][k * C + threadIdx.x]; }
+        atomicAdd(stats + 2 * threadIdx.x, (double)a);
+        atomicAdd(stats + 2 * threadIdx.x + 1, (double)b);
     }
 }
 

@@ -253,80 +253,109 @@ class GMFlow:
         self._chk(lambda: L.drba_gmflow_ln_residual(ptr(x), ptr(m2), ptr(e["g2"]), ptr(e["b2"]), ptr(x), 2, h, w, C, 0, 0, 0, 0, self.st()), "ln_residual")
 
     # ---------------------------------------------------------------- forward
-    def __call__(self, img0, img1):
+    def _match_and_propagate(self, src, tgt, flow, h, w, radius, prop_r, s):
+        """correlation soft-argmax (matching.py) + flow propagation by self-attention on `src` (transformer.py:332-409).
+        src / tgt: [h][w][C] token maps; flow: running flow or None.  Returns the propagated flow [1,2,h,w]."""
+        L, dev, dbg = self.L, self.device, self.debug
+        n = h * w
+        pred = torch.empty((1, 2, h, w), dtype=torch.float32, device=dev)
+        if radius < 0:      # global matching (matching.py:7-43)
+            S = self.buf(("corr", h, w), (1, n, _pad16(n)))
+            run_program([Step(_Operand(tgt.reshape(1, n, C), n, _pad16(n), C), 1, n, [src.reshape(1, n, C)], [S], 1, n, _pad16(n),
+                              act=ACT_NONE, bgemm=1)], dev, tag="gmflow.corr")
+            self._chk(lambda: L.drba_gmflow_soft_readout(ptr(S), n, n, _pad16(n), None, w, 1, 1.0 / math.sqrt(C), ptr(pred), self.st()), "soft_readout")
+        else:
+            self._chk(lambda: L.drba_gmflow_local_match(ptr(src), ptr(tgt), h, w, C, radius, ptr(pred), self.st()), "local_match")
+        if flow is None:
+            flow = pred
+        else:
+            tot = torch.empty_like(pred)
+            self._chk(lambda: L.drba_axpby_f32(ptr(flow), 1.0, ptr(pred), 1.0, ptr(tot), pred.numel(), self.st()), "axpby")
+            flow = tot
+        if dbg is not None:
+            dbg[f"match{s}"] = flow.clone()
+        q = self.buf(("pq", h, w), (h, w, C))
+        kq = self.buf(("pk", h, w), (h, w, C))
+        out = torch.empty_like(flow)
+        if prop_r < 0:      # note: k = k_proj(q_proj(x)) in the global branch (transformer.py:355-356)
+            run_program([Step(self.prop_q, h, w, [src], [q], h, w, C, act=ACT_NONE),
+                         Step(self.prop_k, h, w, [q], [kq], h, w, C, act=ACT_NONE)], dev, tag="gmflow.prop")
+            S = self.buf(("corr", h, w), (1, n, _pad16(n)))
+            run_program([Step(_Operand(kq.reshape(1, n, C), n, _pad16(n), C), 1, n, [q.reshape(1, n, C)], [S], 1, n, _pad16(n),
+                              act=ACT_NONE, bgemm=1)], dev, tag="gmflow.corr")
+            val = flow.reshape(2, n).t().contiguous()            # [n][2] value table (layout plumbing)
+            self._chk(lambda: L.drba_gmflow_soft_readout(ptr(S), n, n, _pad16(n), ptr(val), w, 0, 1.0 / math.sqrt(C), ptr(out), self.st()), "soft_readout")
+        else:
+            run_program([Step(self.prop_q, h, w, [src], [q], h, w, C, act=ACT_NONE),
+                         Step(self.prop_k, h, w, [src], [kq], h, w, C, act=ACT_NONE)], dev, tag="gmflow.prop")
+            self._chk(lambda: L.drba_gmflow_local_propagate(ptr(q), ptr(kq), ptr(flow), h, w, C, ptr(out), self.st()), "local_propagate")
+        if dbg is not None:
+            dbg[f"prop{s}"] = out.clone()
+        return out
+
+    def _refine_and_upsample(self, f4, d, flow8):
+        """Scale 1 (1/4 resolution) for direction d (0: img0 -> img1, 1: img1 -> img0) and the convex upsampling."""
+        L, dev, dbg = self.L, self.device, self.debug
+        h, w, k = f4.shape[1], f4.shape[2], 8
+        x = self.buf(("x", 1, h, w), (2, h, w, C))
+        x[0].copy_(f4[d])
+        up = resize_bilinear(flow8, size=(h, w), align_corners=True)         # gmflow.py:117-119
+        flow = torch.empty_like(up)
+        self._chk(lambda: L.drba_axpby_f32(ptr(up), 2.0, None, 0.0, ptr(flow), up.numel(), self.st()), "axpby")
+        self._chk(lambda: L.drba_gmflow_warp_feature(ptr(f4[1 - d]), ptr(flow), ptr(x[1]), h, w, C, self.st()), "warp_feature")
+        pos = self._pos_table(h // k, w // k)
+        self._chk(lambda: L.drba_gmflow_add_position(ptr(x), ptr(pos), 2, h, w, h // k, w // k, C, self.st()), "add_position")
+        self.transformer_ref_order(x, h, w, k)
+        if dbg is not None:
+            dbg["tf1"] = x.clone()
+        flow = self._match_and_propagate(x[0], x[1], flow, h, w, 4, 1, 1)
+        # convex upsampling x4 (gmflow.py:68-90)
+        xin = self.buf(("upin", h, w), (h, w, 144))
+        self._chk(lambda: L.drba_gmflow_upsampler_input(ptr(flow), ptr(x[0]), ptr(xin), h, w, self.st()), "upsampler_input")
+        hid = self.buf(("uphid", h, w), (h, w, 256))
+        mask = self.buf(("upmask", h, w), (h, w, 144))
+        run_program([Step(self.up0, h, w, [xin], [hid], h, w, 256, act=ACT_RELU),
+                     Step(self.up2, h, w, [hid], [mask], h, w, 144, act=ACT_NONE)], dev, tag="gmflow.upsampler")
+        out = torch.empty((1, 2, 4 * h, 4 * w), dtype=torch.float32, device=dev)
+        self._chk(lambda: L.drba_gmflow_convex_upsample(ptr(mask), ptr(flow), ptr(out), h, w, self.st()), "convex_upsample")
+        return out
+
+    def _forward(self, img0, img1, both):
         require_cuda(img0, img1)
         _, _, H, W = img0.shape
         if H % 32 != 0 or W % 32 != 0:
             raise _lib.DrbaError("GMFlow input must be a multiple of 32 (two 1/8 windows, eight 1/4 windows)")
-        L, dev = self.L, self.device
-        dbg = self.debug
+        L, dev, dbg = self.L, self.device, self.debug
         with torch.cuda.device(dev):
             f8, f4 = self.backbone([img0, img1])
             if dbg is not None:
                 dbg["feat8"] = f8.clone()
                 dbg["feat4"] = f4.clone()
-            flow = None
-            for s, (feat, k, radius, prop_r) in enumerate(((f8, 2, -1, -1), (f4, 8, 4, 1))):
-                h, w = feat.shape[1], feat.shape[2]
-                x = self.buf(("x", s, h, w), (2, h, w, C))
-                x.copy_(feat)
-                if flow is not None:
-                    up = resize_bilinear(flow, size=(h, w), align_corners=True)
-                    flow = torch.empty_like(up)
-                    self._chk(lambda: L.drba_axpby_f32(ptr(up), 2.0, None, 0.0, ptr(flow), up.numel(), self.st()), "axpby")
-                    self._chk(lambda: L.drba_gmflow_warp_feature(ptr(feat[1]), ptr(flow), ptr(x[1]), h, w, C, self.st()), "warp_feature")
-                pos = self._pos_table(h // k, w // k)
-                self._chk(lambda: L.drba_gmflow_add_position(ptr(x), ptr(pos), 2, h, w, h // k, w // k, C, self.st()), "add_position")
-                self.transformer_ref_order(x, h, w, k)
-                if dbg is not None:
-                    dbg[f"tf{s}"] = x.clone()
-                n = h * w
-                pred = torch.empty((1, 2, h, w), dtype=torch.float32, device=dev)
-                if radius < 0:      # global matching (matching.py:7-43)
-                    S = self.buf(("corr", h, w), (1, n, _pad16(n)))
-                    run_program([Step(_Operand(x[1].reshape(1, n, C), n, _pad16(n), C), 1, n, [x[0].reshape(1, n, C)], [S], 1, n, _pad16(n),
-                                      act=ACT_NONE, bgemm=1)], dev, tag="gmflow.corr")
-                    self._chk(lambda: L.drba_gmflow_soft_readout(ptr(S), n, n, _pad16(n), None, w, 1, 1.0 / math.sqrt(C), ptr(pred), self.st()), "soft_readout")
-                else:
-                    self._chk(lambda: L.drba_gmflow_local_match(ptr(x[0]), ptr(x[1]), h, w, C, radius, ptr(pred), self.st()), "local_match")
-                if flow is None:
-                    flow = pred
-                else:
-                    tot = torch.empty_like(pred)
-                    self._chk(lambda: L.drba_axpby_f32(ptr(flow), 1.0, ptr(pred), 1.0, ptr(tot), pred.numel(), self.st()), "axpby")
-                    flow = tot
-                if dbg is not None:
-                    dbg[f"match{s}"] = flow.clone()
-                # flow propagation by self-attention on feature0 (transformer.py:332-409)
-                q = self.buf(("pq", h, w), (h, w, C))
-                kq = self.buf(("pk", h, w), (h, w, C))
-                out = torch.empty_like(flow)
-                if prop_r < 0:
-                    run_program([Step(self.prop_q, h, w, [x[0]], [q], h, w, C, act=ACT_NONE),
-                                 Step(self.prop_k, h, w, [q], [kq], h, w, C, act=ACT_NONE)], dev, tag="gmflow.prop")
-                    S = self.buf(("corr", h, w), (1, n, _pad16(n)))
-                    run_program([Step(_Operand(kq.reshape(1, n, C), n, _pad16(n), C), 1, n, [q.reshape(1, n, C)], [S], 1, n, _pad16(n),
-                                      act=ACT_NONE, bgemm=1)], dev, tag="gmflow.corr")
-                    val = flow.reshape(2, n).t().contiguous()            # [n][2] value table (layout plumbing)
-                    self._chk(lambda: L.drba_gmflow_soft_readout(ptr(S), n, n, _pad16(n), ptr(val), w, 0, 1.0 / math.sqrt(C), ptr(out), self.st()), "soft_readout")
-                else:
-                    run_program([Step(self.prop_q, h, w, [x[0]], [q], h, w, C, act=ACT_NONE),
-                                 Step(self.prop_k, h, w, [x[0]], [kq], h, w, C, act=ACT_NONE)], dev, tag="gmflow.prop")
-                    self._chk(lambda: L.drba_gmflow_local_propagate(ptr(q), ptr(kq), ptr(flow), h, w, C, ptr(out), self.st()), "local_propagate")
-                flow = out
-                if dbg is not None:
-                    dbg[f"prop{s}"] = flow.clone()
-            # convex upsampling x4 (gmflow.py:68-90)
-            h, w = flow.shape[2], flow.shape[3]
-            xin = self.buf(("upin", h, w), (h, w, 144))
-            self._chk(lambda: L.drba_gmflow_upsampler_input(ptr(flow), ptr(x[0]), ptr(xin), h, w, self.st()), "upsampler_input")
-            hid = self.buf(("uphid", h, w), (h, w, 256))
-            mask = self.buf(("upmask", h, w), (h, w, 144))
-            run_program([Step(self.up0, h, w, [xin], [hid], h, w, 256, act=ACT_RELU),
-                         Step(self.up2, h, w, [hid], [mask], h, w, 144, act=ACT_NONE)], dev, tag="gmflow.upsampler")
-            out = torch.empty((1, 2, 4 * h, 4 * w), dtype=torch.float32, device=dev)
-            self._chk(lambda: L.drba_gmflow_convex_upsample(ptr(mask), ptr(flow), ptr(out), h, w, self.st()), "convex_upsample")
-        return out
+            # scale 0 (1/8 resolution, 2 x 2 windows, global matching).  The transformer runs both directions side
+            # by side (transformer.py:294-305), so its output serves flow(img0 -> img1) AND flow(img1 -> img0):
+            # the reference's second call GMFlow(img1, img0) recomputes exactly these features with the halves swapped
+            h, w, k = f8.shape[1], f8.shape[2], 2
+            x = self.buf(("x", 0, h, w), (2, h, w, C))
+            x.copy_(f8)
+            pos = self._pos_table(h // k, w // k)
+            self._chk(lambda: L.drba_gmflow_add_position(ptr(x), ptr(pos), 2, h, w, h // k, w // k, C, self.st()), "add_position")
+            self.transformer_ref_order(x, h, w, k)
+            if dbg is not None:
+                dbg["tf0"] = x.clone()
+            outs = []
+            for d in ((0, 1) if both else (0,)):
+                flow8 = self._match_and_propagate(x[d], x[1 - d], None, h, w, -1, -1, 0)
+                outs.append(self._refine_and_upsample(f4, d, flow8))
+        return outs
+
+    def __call__(self, img0, img1):
+        """flow img0 -> img1, [1,2,H,W] fp32 (models/gmflow/gmflow.py:92-185)."""
+        return self._forward(img0, img1, False)[0]
+
+    def pair(self, img0, img1):
+        """(flow img0 -> img1, flow img1 -> img0): what Model.reuse obtains from two GMFlow calls
+        (models/model_gmfss/GMFSS.py:73-74), sharing the backbone and the 1/8-scale transformer between them."""
+        return tuple(self._forward(img0, img1, True))
 
     def transformer_ref_order(self, x, h, w, k):
         """The reference updates `concat1` (the cross-attention targets) only AFTER a whole block

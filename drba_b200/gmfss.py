@@ -73,8 +73,11 @@ class Model:
             imgf1 = resize_bilinear(img1h, scale_factor=scale)
         else:
             imgf0, imgf1 = img0h, img1h
-        flow01 = self.flow_estimator(imgf0, imgf1)
-        flow10 = self.flow_estimator(imgf1, imgf0)
+        if hasattr(self.flow_estimator, "pair"):      # native GMFlow: both directions share backbone + 1/8-scale transformer
+            flow01, flow10 = self.flow_estimator.pair(imgf0, imgf1)
+        else:
+            flow01 = self.flow_estimator(imgf0, imgf1)
+            flow10 = self.flow_estimator(imgf1, imgf0)
         if scale != 1.0:
             flow01 = self._scaled(resize_bilinear(flow01, scale_factor=1. / scale), 1. / scale)
             flow10 = self._scaled(resize_bilinear(flow10, scale_factor=1. / scale), 1. / scale)

@@ -124,6 +124,21 @@ def test_gmflow_stages_vs_oracle():
     assert report["flow_mean_abs_err"] < 0.1 and report["flow_max_abs_err"] < 1.5
 
 
+def test_gmflow_pair_equals_two_calls():
+    """GMFlow.pair shares the backbone and the 1/8-scale transformer between the two directions; the reference's two
+    independent calls compute the same numbers (transformer.py:294-305 runs both directions side by side)."""
+    from drba_b200.gmflow import GMFlow
+    sd, _ = _state()
+    frames = _frames()
+    with torch.no_grad():
+        net = GMFlow(sd, "cuda")
+        a = net(frames[1], frames[0]).clone()
+        b = net(frames[0], frames[1]).clone()
+        pa, pb = net.pair(frames[1], frames[0])
+    # identical inputs, deterministic kernels (fixed tile order, fixed-order InstanceNorm reduction): bit-identical
+    assert torch.equal(pa, a) and torch.equal(pb, b)
+
+
 def test_gmfss_window_with_native_gmflow(gg=None):
     """GMFSS.inference_ts_drba end to end (native GMFlow + FeatureNet + MetricNet + splats + GridNet) against the
     reference's fp32 window (tests/golden/gmfss_golden.npz, trained weights only)."""
