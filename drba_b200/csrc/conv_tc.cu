@@ -187,6 +187,9 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
 
 #define TC_TRACE(slot) do { if (trace && blockIdx.x == 0) trace[(slot)] = clock64(); } while (0)
 
+// FULL = false: the IFNet / GMFlow feature set (one output, one residual, act none / LeakyReLU / ReLU / GELU);
+// FULL = true adds the GMFSS epilogue (second residual, up to three outputs, PReLU variants) at a higher register cost
+template <bool FULL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ Program prog)
 {
@@ -471,10 +474,10 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                         const size_t pix = os == 1 ? (size_t)oy * OW + ox
                                                    : (size_t)(oy * os + (g >> 1)) * (OW * os) + (ox * os + (g & 1));
                         __half* out = reinterpret_cast<__half*>(L.out[img]) + pix * cstride + nbase;
-                        __half* out1 = L.out1[img] ? reinterpret_cast<__half*>(L.out1[img]) + pix * cstride + nbase : nullptr;
-                        __half* out2 = L.out2[img] ? reinterpret_cast<__half*>(L.out2[img]) + pix * cstride + nbase : nullptr;
+                        __half* out1 = (FULL && L.out1[img]) ? reinterpret_cast<__half*>(L.out1[img]) + pix * cstride + nbase : nullptr;
+                        __half* out2 = (FULL && L.out2[img]) ? reinterpret_cast<__half*>(L.out2[img]) + pix * cstride + nbase : nullptr;
                         const __half* res = (resb && valid && !(dbg & 16)) ? resb + pix * cstride + nbase : nullptr;
-                        const __half* res2 = (L.res2[img] && valid) ? L.res2[img] + pix * cstride + nbase : nullptr;
+                        const __half* res2 = (FULL && L.res2[img] && valid) ? L.res2[img] + pix * cstride + nbase : nullptr;
                         for (int c0 = 0; c0 < ntile; c0 += 32) {
                             uint32_t rr[32];
                             tc_ld16_nowait(taddr + c0, rr);
@@ -523,7 +526,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                                 }
                                 // up to three outputs of the same pre-activation value, each with its own activation
 #pragma unroll
-                                for (int oi = 0; oi < 3; ++oi) {
+                                for (int oi = 0; oi < (FULL ? 3 : 1); ++oi) {
                                     __half* op = oi == 0 ? out : (oi == 1 ? out1 : out2);
                                     if (!op) continue;
                                     const int a = oi == 0 ? act : (oi == 1 ? act1 : act2);
@@ -532,7 +535,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                                     if (a == 0) {
 #pragma unroll
                                         for (int i = 0; i < 16; ++i) w[i] = v[i];
-                                    } else if (a == 2) {
+                                    } else if (FULL && a == 2) {
 #pragma unroll
                                         for (int i = 0; i < 16; ++i) w[i] = v[i] > 0.0f ? v[i] : s_slope[nbase + c + i] * v[i];
                                     } else if (a == 5) {      // exact GELU (nn.GELU default)
@@ -860,8 +863,16 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
     static bool attr_set = false;
     const size_t smem = (size_t)kBRegion + (size_t)kStages * kABytesMax + 1024;   // == kStages * kStageBytes + 1024
     if (!attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
+    }
+    bool full = false;
+    for (int i = 0; i < nlayers; ++i) {
+        const drba_conv_layer& d = layers[i];
+        if (d.act == 2 || d.act == 4 || d.act1 || d.act2) full = true;
+        for (int k = 0; k < nimg; ++k)
+            if (d.res2[k] || d.out1[k] || d.out2[k]) full = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -873,7 +884,7 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = env_pdl ? 1 : 0;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel, prog);
+    const cudaError_t le = full ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, prog) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, prog);
     if (le != cudaSuccess) return (int)le;
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
