@@ -316,3 +316,34 @@ def test_softsplat_gather_path_bit_exact_vs_oracle(mode, shape):
         assert np.array_equal(got, want, equal_nan=True), f"max |diff| {np.nanmax(np.abs(got - want))}"
     ws = Workspace.get(1, torch.device("cuda", torch.cuda.current_device()))
     assert int(ws.count_nonzero().item()) == 0, "workspace must be all-zero on exit"
+
+
+@pytest.mark.parametrize("s,H,W", [(1, 64, 96), (2, 64, 96), (4, 96, 160), (8, 64, 128), (2, 36, 44)])
+@pytest.mark.parametrize("ts_map", [False, True])
+def test_ifnet_assemble_coalesced_kernel_matches_per_pixel_kernel(monkeypatch, s, H, W, ts_map):
+    """The L1-friendly block-input kernel (lane pairs / shuffled 2x2 means / staged row stores) must
+    reproduce the one-lane-per-pixel kernel bit for bit (IFNet_HDv3.py:151-155 + :87-88)."""
+    from drba_b200._lib import lib, check
+    from drba_b200._torch_util import ptr, stream_ptr
+    L = lib()
+    g = torch.Generator(device="cuda").manual_seed(100 * s + H)
+    img0 = torch.rand(3, H, W, device="cuda", generator=g)
+    img1 = torch.rand(3, H, W, device="cuda", generator=g)
+    f0 = torch.randn(H, W, 16, device="cuda", generator=g).half()
+    f1 = torch.randn(H, W, 16, device="cuda", generator=g).half()
+    flow = 6.0 * torch.randn(H, W, 4, device="cuda", generator=g)
+    flow[: H // 4] *= 20.0                      # taps clamped at the borders
+    sp = 2 * s
+    prev = torch.randn(H // sp, W // sp, 16, device="cuda", generator=g)
+    ts = torch.rand(H, W, device="cuda", generator=g) if ts_map else None
+    outs = []
+    for v1 in ("1", "0"):
+        monkeypatch.setenv("DRBA_ASSEMBLE_V1", v1)
+        out = torch.full((H // s, W // s, 64), float("nan"), device="cuda", dtype=torch.float16)
+        rc = L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 1, ptr(ts) if ts_map else None, 0.37,
+                                   ptr(flow), ptr(prev), 1, sp, ptr(out), 1, 64, H, W, s, stream_ptr("cuda"))
+        check(rc, "drba_ifnet_assemble")
+        torch.cuda.synchronize()
+        outs.append(out.view(torch.int16).cpu().numpy())
+    assert np.isfinite(outs[1].view(np.float16)).all()
+    np.testing.assert_array_equal(outs[0], outs[1])
