@@ -165,6 +165,41 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int swz_bytes) {
 // one lane of a converged warp, chosen by the hardware: keeps the surrounding control flow warp-uniform so
 // that TMA / MMA operands stay in uniform registers (a plain `lane == 0` branch makes the compiler
 // wrap every UTMALDG / UTCHMMA in an R2UR waterfall loop, ~150 cycles per instruction)
+// MMA issue loops, K steps unrolled.  Descriptor start addresses are (addr >> 4) in the low 14 bits: advancing
+// 16 fp16 = 32 bytes along K inside the swizzle span is +2, and shared memory (< 256 KB) never carries out of
+// the field, so offsets are plain 64-bit adds.
+template <int KS>
+__device__ __forceinline__ void issue_tile(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t a_mt16, int MT, int ntile,
+                                           uint32_t idesc, uint32_t accumulate)
+{
+    for (int mt = 0; mt < MT; ++mt) {
+        const uint64_t da = da0 + (uint64_t)(mt * a_mt16);
+#pragma unroll
+        for (int k = 0; k < KS; ++k)
+            tc_mma_f16(tmem_d + mt * ntile, da + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
+    }
+}
+
+// halo mode (canonical 3x3 taps, checked on the host): tap (ty, tx) of M tile mt starts at halo pixel
+// ((mt * 16 + ty) * 16 + tx); the tap's weight tile is b_tap16 further on
+template <int KS>
+__device__ __forceinline__ void issue_halo(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t rowb16, uint32_t b_tap16,
+                                           int MT, int ntile, uint32_t idesc, uint32_t accumulate)
+{
+    for (int mt = 0; mt < MT; ++mt) {
+        const uint64_t da_mt = da0 + (uint64_t)((uint32_t)(mt * 256) * rowb16);
+        const uint32_t d = tmem_d + mt * ntile;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t da = da_mt + (uint64_t)((uint32_t)((tap / 3) * 16 + tap % 3) * rowb16);
+            const uint64_t db = db0 + (uint64_t)((uint32_t)tap * b_tap16);
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+                tc_mma_f16(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)(tap | k));
+        }
+    }
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile("{\n\t.reg .pred p;\n\t"
@@ -366,7 +401,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             // halo mode: rows of an 8-pixel tile row are contiguous, tile rows are 16 pixels apart in the halo tile
             const uint32_t rowb16 = (uint32_t)(Kc * 2) >> 4;
             const uint64_t desc_hi_halo = (desc_hi & ~(0x3FFFull << 32)) | ((uint64_t)(16u * rowb16) << 32);
-            const int halo_bo = L.halo_bo;
+            const uint32_t b_tap16 = (uint32_t)kchunks * b_sub16;
             const uint32_t a_base16 = (a_base & 0x3FFFFu) >> 4, a_stride16 = a_stride >> 4;
             const uint32_t b_res16 = (smem & 0x3FFFFu) >> 4;
             if (resident && total_tiles > (int)blockIdx.x) {
@@ -389,35 +424,27 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                     tc_fence_after();
                     if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 2);
                     const uint32_t sa16 = a_base16 + stage * a_stride16;
-                    if (halo) {
-                        if (elect_one()) {
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const int e = L.tapc[0][tap];
-                                const int dy = (e & 0xff) - 64, dx = ((e >> 8) & 0xff) - 64;
-                                const uint64_t db = desc_hi | (uint64_t)(b_tile16 + (uint32_t)(tap * kchunks + it) * b_sub16);
-                                for (int mt = 0; mt < MT; ++mt) {
-                                    const uint32_t start16 = sa16 + (uint32_t)((mt * 16 + dy + 1) * 16 + dx + 1) * rowb16;
-                                    uint64_t da = desc_hi_halo | (uint64_t)start16;
-                                    if (halo_bo) da |= (uint64_t)((start16 >> 3) & 7u) << 49;
-                                    for (int k = 0; k < ksteps; ++k)
-                                        tc_mma_f16(tmem_d + mt * ntile, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)(tap | k));
-                                }
+                    if (elect_one()) {
+                        if (halo) {
+                            const uint64_t da0 = desc_hi_halo | (uint64_t)sa16;
+                            const uint64_t db0 = desc_hi | (uint64_t)(b_tile16 + (uint32_t)it * b_sub16);
+                            switch (ksteps) {
+                                case 1: issue_halo<1>(tmem_d, da0, db0, rowb16, b_tap16, MT, ntile, idesc, accumulate); break;
+                                case 2: issue_halo<2>(tmem_d, da0, db0, rowb16, b_tap16, MT, ntile, idesc, accumulate); break;
+                                case 4: issue_halo<4>(tmem_d, da0, db0, rowb16, b_tap16, MT, ntile, idesc, accumulate); break;
+                                default: break;
                             }
-                            tc_commit(&empty_bar[stage]);
-                        }
-                    } else {
-                        const uint32_t sb16 = resident ? b_tile16 + (uint32_t)it * b_sub16 : sa16 + (kABytesMax >> 4);
-                        if (elect_one()) {
-                            const uint64_t db = desc_hi | (uint64_t)sb16;
-                            for (int mt = 0; mt < MT; ++mt) {
-                                const uint64_t da = desc_hi | (uint64_t)(sa16 + mt * a_mt16);
-                                for (int k = 0; k < ksteps; ++k) {
-                                    // advance 16 fp16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
-                                    tc_mma_f16(tmem_d + mt * ntile, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
-                                }
+                        } else {
+                            const uint32_t sb16 = resident ? b_tile16 + (uint32_t)it * b_sub16 : sa16 + (kABytesMax >> 4);
+                            const uint64_t da0 = desc_hi | (uint64_t)sa16, db0 = desc_hi | (uint64_t)sb16;
+                            switch (ksteps) {
+                                case 1: issue_tile<1>(tmem_d, da0, db0, a_mt16, MT, ntile, idesc, accumulate); break;
+                                case 2: issue_tile<2>(tmem_d, da0, db0, a_mt16, MT, ntile, idesc, accumulate); break;
+                                case 4: issue_tile<4>(tmem_d, da0, db0, a_mt16, MT, ntile, idesc, accumulate); break;
+                                default: break;
                             }
-                            tc_commit(&empty_bar[stage]);
                         }
+                        tc_commit(&empty_bar[stage]);
                     }
                     __syncwarp();
                     accumulate = 1;
