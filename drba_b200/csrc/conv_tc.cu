@@ -281,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
         asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[0].ta[0]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[0].tb) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
         mbar_init(&b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -465,15 +465,21 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             const int OH = L.OH, OW = L.OW, cout = L.cout, cout_pad = L.cout_pad, act = L.act;
             const int epilogue = L.epilogue, os = L.os, cstride = L.out_cstride, act1 = L.act1, act2 = L.act2;
             const float slope0 = L.slope0, slope1 = L.slope1, slope2 = L.slope2;
+            // Both groups work on EVERY tile (half of the accumulator each), so a tile's drain latency is halved and
+            // layers with one or two tiles per SM do not leave a group idle: M tiles split when the super tile
+            // stacks several, columns split otherwise.
+            const int mt_lo = MT >= 2 ? (int)group * (MT >> 1) : 0, mt_hi = MT >= 2 ? mt_lo + (MT >> 1) : 1;
+            const int chalf = ((ntile >> 1) + 15) & ~15;
+            const int c_lo = MT >= 2 ? 0 : (group ? chalf : 0), c_hi = MT >= 2 ? ntile : (group ? ntile : chalf);
             for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount) {
                 const uint32_t buf = tcount & 1u, use = tcount >> 1;
-                if (buf != group) continue;
                 const int m = idx % mtiles;
                 int r = idx / mtiles;
                 const int nsplit = r % nsplits; r /= nsplits;
                 const int g = r % G, img = r / G;
                 const int ty = m / tiles_x;
                 const int oy_s = ty * tile_h * MT + ry, ox = (m - ty * tiles_x) * tile_w + rx;
+                const int oy_f = oy_s + mt_lo * tile_h;      // this group's first M tile
                 const int nbase = nsplit * ntile;
                 const bool has_bias = L.has_bias != 0;
                 const float* bias = s_bias + (has_bias ? g * cout_pad + nbase : 0);
@@ -482,18 +488,18 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 // the residual does not depend on the accumulator: fetch (up to) 32 channels of the first M tile before waiting
                 uint4 rpre[4];
                 {
-                    const bool v0 = oy_s < OH && ox < OW;
+                    const bool v0 = oy_f < OH && ox < OW;
                     if (resb && v0) {
-                        const __half* res = resb + ((size_t)oy_s * OW + ox) * cstride + nbase;
+                        const __half* res = resb + ((size_t)oy_f * OW + ox) * cstride + nbase + c_lo;
 #pragma unroll
                         for (int h = 0; h < 4; ++h)
-                            if (h * 8 < ntile) rpre[h] = reinterpret_cast<const uint4*>(res)[h];
+                            if (c_lo + h * 8 < c_hi) rpre[h] = reinterpret_cast<const uint4*>(res)[h];
                     }
                 }
                 mbar_wait(&acc_full[buf], use & 1u);
                 tc_fence_after();
                 if (idx == blockIdx.x && q == 2 && lane == 0) TC_TRACE(li * 256 + 200);
-                for (int mt = 0; mt < MT; ++mt) {
+                for (int mt = mt_lo; mt < mt_hi; ++mt) {
                     const int oy = oy_s + mt * tile_h;
                     const bool valid = oy < OH && ox < OW;
                     const uint32_t taddr = taddr0 + (uint32_t)(mt * ntile);
@@ -505,17 +511,17 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                         __half* out2 = (FULL && L.out2[img]) ? reinterpret_cast<__half*>(L.out2[img]) + pix * cstride + nbase : nullptr;
                         const __half* res = (resb && valid && !(dbg & 16)) ? resb + pix * cstride + nbase : nullptr;
                         const __half* res2 = (FULL && L.res2[img] && valid) ? L.res2[img] + pix * cstride + nbase : nullptr;
-                        for (int c0 = 0; c0 < ntile; c0 += 32) {
+                        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
                             uint32_t rr[32];
                             tc_ld16_nowait(taddr + c0, rr);
-                            if (c0 + 16 < ntile) tc_ld16_nowait(taddr + c0 + 16, rr + 16);
+                            if (c0 + 16 < c_hi) tc_ld16_nowait(taddr + c0 + 16, rr + 16);
                             tc_ld_wait();
-                            if (idx == blockIdx.x && q == 2 && lane == 0 && mt == 0) TC_TRACE(li * 256 + 204 + (c0 >> 5) * 2);
+                            if (idx == blockIdx.x && q == 2 && lane == 0 && mt == 0) TC_TRACE(li * 256 + 204 + ((c0 - c_lo) >> 5) * 2);
                             if (!valid) continue;
 #pragma unroll
                             for (int hh = 0; hh < 2; ++hh) {
                                 const int c = c0 + hh * 16;
-                                if (c >= ntile || nbase + c >= cout) continue;
+                                if (c >= c_hi || nbase + c >= cout) continue;
                                 float v[16];
 #pragma unroll
                                 for (int i = 0; i < 16; i += 4) {
@@ -529,7 +535,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
 #pragma unroll
                                     for (int h = 0; h < 2; ++h) {
                                         uint4 rv;
-                                        if (mt == 0 && c0 == 0) rv = rpre[hh * 2 + h];
+                                        if (mt == mt_lo && c0 == c_lo) rv = rpre[hh * 2 + h];
                                         else rv = reinterpret_cast<const uint4*>(res + c)[h];
                                         const __half2* hp = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
@@ -580,7 +586,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                                     if (!(dbg & 8)) { o4[0] = o[0]; o4[1] = o[1]; }
                                 }
                             }
-                            if (idx == blockIdx.x && q == 2 && lane == 0 && mt == 0) TC_TRACE(li * 256 + 205 + (c0 >> 5) * 2);
+                            if (idx == blockIdx.x && q == 2 && lane == 0 && mt == 0) TC_TRACE(li * 256 + 205 + ((c0 - c_lo) >> 5) * 2);
                         }
                     } else {
                         // lastconv: group g = phase (py, px); channel co = c13*4 + i*2 + j lands at
@@ -588,7 +594,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                         const int py = g >> 1, px = g & 1;
                         const int OW4 = OW * 4;
                         float* out = reinterpret_cast<float*>(L.out[img]);
-                        for (int c0 = 0; c0 < 64; c0 += 32) {
+                        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {      // ntile == 64 (checked on the host)
                             uint32_t rr[32];
                             tc_ld16_nowait(taddr + c0, rr);
                             tc_ld16_nowait(taddr + c0 + 16, rr + 16);
