@@ -77,6 +77,7 @@ struct alignas(64) LayerDev {
     int nst;                // ring stages used by this layer
     int a_base, a_stride;   // byte offset of the activation ring and bytes per stage
     int halo_bo;            // experiment: write the descriptor's base_offset field
+    int pack;               // packed halo mode: pixels per 128-byte line (2 or 4), else 1
     int ntile, nsplits, cout_pad, cout;
     int swz_bytes;          // 32 / 64 / 128
     int b_sub;              // bytes of one weight tile (padded to the swizzle period)
@@ -200,6 +201,32 @@ __device__ __forceinline__ void issue_halo(uint32_t tmem_d, uint64_t da0, uint64
     }
 }
 
+// packed halo mode (Cin = 32 or 16: P = 2 or 4 pixels share one 128-byte line; the halo box is 10 lines x 18 rows
+// for an 8P x 16 pixel tile).  M tile p holds the output pixels x = x0 + P * j + p (j = 0..7, 16 rows): for tap
+// (ty, tx) its operand rows are the input pixels x0 - P + P * j + (p + tx - 1 + P), i.e. line j + q / P of halo row
+// iy + ty at byte q % P * Kc * 2 inside the line -- a K offset inside the 128-byte swizzle span, like the k * 2
+// advance.  Eight consecutive lines are one core group; the next image row is 10 lines further (SBO = 1280 B).
+template <int P>
+__device__ __forceinline__ void issue_halo_packed(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t b_tap16, int ntile,
+                                                  uint32_t idesc, uint32_t accumulate)
+{
+    constexpr int KS = 4 / P;            // Kc = 64 / P channels = KS steps of 16
+    constexpr int SUB16 = 8 / P;         // one pixel inside the line, in 16-byte units
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const uint32_t d = tmem_d + p * ntile;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int q = p + tap % 3 - 1 + P;
+            const uint64_t da = da0 + (uint64_t)(((tap / 3) * 10 + q / P) * 8 + (q % P) * SUB16);
+            const uint64_t db = db0 + (uint64_t)((uint32_t)tap * b_tap16);
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+                tc_mma_f16(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)(tap | k));
+        }
+    }
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile("{\n\t.reg .pred p;\n\t"
@@ -314,34 +341,36 @@ conv_tc_kernel(const __grid_constant__ Program prog)
         const int KI = L.KI, T = L.T, ntile = L.ntile, kchunks = L.kchunks, Kc = L.Kc, resident = L.resident;
         const uint32_t a_base = smem + (uint32_t)L.a_base;
         const uint32_t a_stride = (uint32_t)L.a_stride;
-        const int nst = L.nst, halo = L.halo;
+        const int nst = L.nst, halo = L.halo, pack = L.pack;
+        const int super_h = pack > 1 ? tile_h : tile_h * MT;     // output rows of one super tile
         stage = 0;
 
         if (warp == 0) {
             // ===== activation producer: the whole warp walks the loop, one elected lane issues =====
-            const uint32_t a_bytes = (dbg & 2) ? 0u : (uint32_t)(halo ? (16 * MT + 2) * 16 * Kc * 2 : MT * kTileM * Kc * 2);
+            const uint32_t a_bytes = (dbg & 2) ? 0u : (uint32_t)(pack > 1 ? 10 * 18 * 128 : (halo ? (16 * MT + 2) * 16 * Kc * 2 : MT * kTileM * Kc * 2));
             if (li + 1 < nlayers && elect_one()) {
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].ta[0]) : "memory");
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].tb) : "memory");
             }
-            for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x) {
+            int tl = 0;
+            for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tl) {
                 const int m = idx % mtiles;
                 int r = idx / mtiles;
                 r /= nsplits;
                 const int g = r % G, img = r / G;
                 const int ty = m / tiles_x;
-                const int oy0 = ty * tile_h * MT, ox0 = (m - ty * tiles_x) * tile_w;
+                const int oy0 = ty * super_h, ox0 = (m - ty * tiles_x) * tile_w;
                 const CUtensorMap* ta = &L.ta[img];
                 int tap = 0, kc = 0;
                 for (int it = 0; it < KI; ++it) {
-                    if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 0);
+                    if (tl < 10 && it < 2 && lane == 0) TC_TRACE(li * 256 + tl * 16 + it * 4 + 0);
                     mbar_wait(&empty_bar[stage], ((pbits >> stage) & 1u) ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(&full_bar[stage], a_bytes);
                         if (resident) mbar_arrive(&full_bar[stage]);      // stands in for the weight producer
                         if (halo) {
                             // one box per K chunk: the (16*MT+2) x 16 pixel neighbourhood of the 8 x 16*MT tile
-                            if (!(dbg & 2)) tma_load_5d(a_base + stage * a_stride, ta, &full_bar[stage], it * Kc, 0, ox0 - 1, 0, oy0 - 1);
+                            if (!(dbg & 2)) tma_load_5d(a_base + stage * a_stride, ta, &full_bar[stage], it * Kc, 0, pack > 1 ? ox0 / pack - 1 : ox0 - 1, 0, oy0 - 1);
                         } else {
                             const int e = L.tapc[g][tap];
                             const int cy = (e & 0xff) - 64, cx = ((e >> 8) & 0xff) - 64, pary = (e >> 16) & 1, parx = (e >> 17) & 1;
@@ -349,7 +378,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                         }
                     }
                     __syncwarp();
-                    if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 1);
+                    if (tl < 10 && it < 2 && lane == 0) TC_TRACE(li * 256 + tl * 16 + it * 4 + 1);
                     if (++kc == kchunks) { kc = 0; ++tap; }
                     pbits ^= 1u << stage;
                     if (++stage == (uint32_t)nst) stage = 0;
@@ -402,6 +431,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             const uint32_t rowb16 = (uint32_t)(Kc * 2) >> 4;
             const uint64_t desc_hi_halo = (desc_hi & ~(0x3FFFull << 32)) | ((uint64_t)(16u * rowb16) << 32);
             const uint32_t b_tap16 = (uint32_t)kchunks * b_sub16;
+            const uint64_t desc_a_packed = (make_desc(0, 128) & ~(0x3FFFull << 32)) | ((uint64_t)(1280u >> 4) << 32);
             const uint32_t a_base16 = (a_base & 0x3FFFFu) >> 4, a_stride16 = a_stride >> 4;
             const uint32_t b_res16 = (smem & 0x3FFFFu) >> 4;
             if (resident && total_tiles > (int)blockIdx.x) {
@@ -409,7 +439,8 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 tc_fence_after();
             }
             if (resident) bres_phase ^= 1u;
-            for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount) {
+            int tl = 0;
+            for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount, ++tl) {
                 const uint32_t buf = tcount & 1u, use = tcount >> 1;
                 int r = idx / mtiles;
                 const int nsplit = r % nsplits; r /= nsplits;
@@ -422,10 +453,16 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 for (int it = 0; it < KI; ++it) {
                     mbar_wait(&full_bar[stage], (pbits >> stage) & 1u);
                     tc_fence_after();
-                    if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 2);
+                    if (tl < 10 && it < 2 && lane == 0) TC_TRACE(li * 256 + tl * 16 + it * 4 + 2);
                     const uint32_t sa16 = a_base16 + stage * a_stride16;
                     if (elect_one()) {
-                        if (halo) {
+                        if (pack > 1) {
+                            const uint64_t da0 = desc_a_packed | (uint64_t)sa16;
+                            const uint64_t db0 = desc_hi | (uint64_t)b_tile16;
+                            if (ksteps == 0) {}
+                            else if (pack == 2) issue_halo_packed<2>(tmem_d, da0, db0, b_tap16, ntile, idesc, accumulate);
+                            else issue_halo_packed<4>(tmem_d, da0, db0, b_tap16, ntile, idesc, accumulate);
+                        } else if (halo) {
                             const uint64_t da0 = desc_hi_halo | (uint64_t)sa16;
                             const uint64_t db0 = desc_hi | (uint64_t)(b_tile16 + (uint32_t)it * b_sub16);
                             switch (ksteps) {
@@ -448,7 +485,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                     }
                     __syncwarp();
                     accumulate = 1;
-                    if (idx == blockIdx.x && it < 48 && lane == 0) TC_TRACE(li * 256 + it * 4 + 3);
+                    if (tl < 10 && it < 2 && lane == 0) TC_TRACE(li * 256 + tl * 16 + it * 4 + 3);
                     pbits ^= 1u << stage;
                     if (++stage == (uint32_t)nst) stage = 0;
                 }
@@ -461,7 +498,8 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             const uint32_t group = (uint32_t)(warp - 2) >> 2;
             const int q = warp & 3;
             const int row = q * 32 + lane;
-            const int ry = row / tile_w, rx = row - ry * tile_w;
+            const int row_w = pack > 1 ? 8 : tile_w;
+            const int ry = row / row_w, rx = row - ry * row_w;
             const int OH = L.OH, OW = L.OW, cout = L.cout, cout_pad = L.cout_pad, act = L.act;
             const int epilogue = L.epilogue, os = L.os, cstride = L.out_cstride, act1 = L.act1, act2 = L.act2;
             const float slope0 = L.slope0, slope1 = L.slope1, slope2 = L.slope2;
@@ -471,15 +509,18 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             const int mt_lo = MT >= 2 ? (int)group * (MT >> 1) : 0, mt_hi = MT >= 2 ? mt_lo + (MT >> 1) : 1;
             const int chalf = ((ntile >> 1) + 15) & ~15;
             const int c_lo = MT >= 2 ? 0 : (group ? chalf : 0), c_hi = MT >= 2 ? ntile : (group ? ntile : chalf);
-            for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount) {
+            int tl = 0;
+            for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount, ++tl) {
                 const uint32_t buf = tcount & 1u, use = tcount >> 1;
                 const int m = idx % mtiles;
                 int r = idx / mtiles;
                 const int nsplit = r % nsplits; r /= nsplits;
                 const int g = r % G, img = r / G;
                 const int ty = m / tiles_x;
-                const int oy_s = ty * tile_h * MT + ry, ox = (m - ty * tiles_x) * tile_w + rx;
-                const int oy_f = oy_s + mt_lo * tile_h;      // this group's first M tile
+                // packed halo mode: M tile mt holds the pixels x = x0 + pack * rx + mt of the same 16 rows
+                const int oy_s = ty * super_h + ry, ox_s = (m - ty * tiles_x) * tile_w + rx * pack;
+                const int mt_dy = pack > 1 ? 0 : tile_h, mt_dx = pack > 1 ? 1 : 0;
+                const int oy_f = oy_s + mt_lo * mt_dy, ox_f = ox_s + mt_lo * mt_dx;      // this group's first M tile
                 const int nbase = nsplit * ntile;
                 const bool has_bias = L.has_bias != 0;
                 const float* bias = s_bias + (has_bias ? g * cout_pad + nbase : 0);
@@ -488,9 +529,9 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 // the residual does not depend on the accumulator: fetch (up to) 32 channels of the first M tile before waiting
                 uint4 rpre[4];
                 {
-                    const bool v0 = oy_f < OH && ox < OW;
+                    const bool v0 = oy_f < OH && ox_f < OW;
                     if (resb && v0) {
-                        const __half* res = resb + ((size_t)oy_f * OW + ox) * cstride + nbase + c_lo;
+                        const __half* res = resb + ((size_t)oy_f * OW + ox_f) * cstride + nbase + c_lo;
 #pragma unroll
                         for (int h = 0; h < 4; ++h)
                             if (c_lo + h * 8 < c_hi) rpre[h] = reinterpret_cast<const uint4*>(res)[h];
@@ -498,9 +539,9 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 }
                 mbar_wait(&acc_full[buf], use & 1u);
                 tc_fence_after();
-                if (idx == blockIdx.x && q == 2 && lane == 0) TC_TRACE(li * 256 + 200);
+                if (tl < 10 && q == 2 && lane == 0) TC_TRACE(li * 256 + tl * 16 + 8 + group * 2);
                 for (int mt = mt_lo; mt < mt_hi; ++mt) {
-                    const int oy = oy_s + mt * tile_h;
+                    const int oy = oy_s + mt * mt_dy, ox = ox_s + mt * mt_dx;
                     const bool valid = oy < OH && ox < OW;
                     const uint32_t taddr = taddr0 + (uint32_t)(mt * ntile);
                     if (epilogue == 0) {
@@ -516,7 +557,6 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                             tc_ld16_nowait(taddr + c0, rr);
                             if (c0 + 16 < c_hi) tc_ld16_nowait(taddr + c0 + 16, rr + 16);
                             tc_ld_wait();
-                            if (idx == blockIdx.x && q == 2 && lane == 0 && mt == 0) TC_TRACE(li * 256 + 204 + ((c0 - c_lo) >> 5) * 2);
                             if (!valid) continue;
 #pragma unroll
                             for (int hh = 0; hh < 2; ++hh) {
@@ -586,7 +626,6 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                                     if (!(dbg & 8)) { o4[0] = o[0]; o4[1] = o[1]; }
                                 }
                             }
-                            if (idx == blockIdx.x && q == 2 && lane == 0 && mt == 0) TC_TRACE(li * 256 + 205 + ((c0 - c_lo) >> 5) * 2);
                         }
                     } else {
                         // lastconv: group g = phase (py, px); channel co = c13*4 + i*2 + j lands at
@@ -616,7 +655,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                         }
                     }
                 }
-                if (idx == blockIdx.x && q == 2 && lane == 0) TC_TRACE(li * 256 + 201);
+                if (tl < 10 && q == 2 && lane == 0) TC_TRACE(li * 256 + tl * 16 + 9 + group * 2);
                 // accumulator drained: hand the buffer back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
@@ -733,10 +772,11 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     // taps as descriptor offsets into it (8-pixel-wide tiles keep every 8-row core group contiguous; the 16-pixel
     // pitch keeps the swizzle phase identical for all groups) -- 4x fewer activation bytes than one box per tap.
     // Needs the weights resident (checked below once ntile is final).
-    static int env_halo = -1, env_halo_bo = -1;
+    static int env_halo = -1, env_halo_bo = -1, env_pack = -1;
     if (env_halo < 0) {
         const char* e = getenv("DRBA_TC_HALO"); env_halo = e ? atoi(e) : 1;
         e = getenv("DRBA_TC_HALO_BO"); env_halo_bo = e ? atoi(e) : 0;
+        e = getenv("DRBA_TC_PACK"); env_pack = e ? atoi(e) : 1;
     }
     bool halo = env_halo && S == 1 && T == 9 && G == 1 && d.epilogue == 0 && !d.bgemm;
     if (halo)
@@ -748,7 +788,15 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     long best = -1;
     int best_mt = 1;
     L.tile_w = 16; L.tile_h = 8;
-    if (halo) {
+    // packed halo mode: thin inputs (16 / 32 channels) put 4 / 2 pixels on one 128-byte line, so the halo box has
+    // 10 x 18 lines for an 8P x 16 pixel tile instead of 16 x (16 MT + 2) short ones (TMA time goes by the line)
+    int pack = 1;
+    if (halo && env_pack && L.kchunks == 1 && L.Kc < 64 && W % (64 / L.Kc) == 0 && ntile * (64 / L.Kc) <= kMaxNTile)
+        pack = 64 / L.Kc;
+    if (pack > 1) {
+        L.tile_w = 8 * pack; L.tile_h = 16;
+        best_mt = pack;
+    } else if (halo) {
         L.tile_w = 8; L.tile_h = 16;
         while (MT > 1 && (OH + 16 * MT - 1) / (16 * MT) * MT * 100 > ((OH + 15) / 16) * 106) MT >>= 1;   // avoid > 6 % more rows
         best_mt = MT;
@@ -772,7 +820,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     MT = best_mt;
     L.MT = MT;
     L.tiles_x = (OW + L.tile_w - 1) / L.tile_w;
-    L.mtiles = L.tiles_x * ((OH + L.tile_h * MT - 1) / (L.tile_h * MT));
+    L.mtiles = L.tiles_x * (pack > 1 ? (OH + 15) / 16 : (OH + L.tile_h * MT - 1) / (L.tile_h * MT));
     // small layers: split N further so that more SMs stream the K loop in parallel
     if (d.epilogue == 0) {
         while (ntile >= 64 && ntile % 32 == 0 && nimg * L.mtiles * G * (d.cout_pad / ntile) * 2 <= kNumSMs) ntile /= 2;
@@ -797,7 +845,8 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     // stages of [A 16 KB | B 16 KB].  Halo mode needs resident weights.
     const long total_smem = (long)kStages * kStageBytes;
     const long w_bytes = ((long)G * L.nsplits * T * L.kchunks * L.b_sub + 1023) / 1024 * 1024;
-    const long a_stage = halo ? (((long)(16 * MT + 2) * 16 * L.Kc * 2 + 1023) / 1024 * 1024) : kABytesMax;
+    const long a_stage = pack > 1 ? (10 * 18 * 128 + 1023) / 1024 * 1024
+                                  : (halo ? (((long)(16 * MT + 2) * 16 * L.Kc * 2 + 1023) / 1024 * 1024) : kABytesMax);
     static int env_res = -1;
     if (env_res < 0) { const char* e = getenv("DRBA_TC_RESIDENT"); env_res = e ? atoi(e) : 1; }
     bool resident = env_res && !d.bgemm && w_bytes + 2 * a_stage <= total_smem && w_bytes <= (long)kBRegion + 32768;
@@ -820,6 +869,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     L.resident = resident ? 1 : 0;
     L.halo = halo ? 1 : 0;
     L.halo_bo = env_halo_bo;
+    L.pack = halo ? pack : 1;
     L.KI = halo ? L.kchunks : T * L.kchunks;
     if (resident) {
         L.a_base = (int)w_bytes;
@@ -831,7 +881,18 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     }
 
     // A: input viewed as [H/S][S][W/S][S][C], innermost first
-    for (int i = 0; i < nimg; ++i) {
+    for (int i = 0; i < nimg && L.pack > 1; ++i) {
+        // packed halo: [H][W / P][P * Cin] with 128-byte lines
+        const cuuint64_t dims[5] = {64, 1, (cuuint64_t)(W / L.pack), 1, (cuuint64_t)H};
+        const cuuint64_t strides[4] = {128, 128, (cuuint64_t)W * Cin * 2, (cuuint64_t)W * Cin * 2};
+        const cuuint32_t box[5] = {64, 1, 10, 1, 18};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const CUresult r = encode(&L.ta[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d.in[i]), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return DRBA_E_UNSUPPORTED;
+    }
+    for (int i = 0; i < nimg && L.pack == 1; ++i) {
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)S, (cuuint64_t)(W / S), (cuuint64_t)S, (cuuint64_t)(H / S)};
         const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)S * Cin * 2, (cuuint64_t)W * Cin * 2,
                                        (cuuint64_t)S * W * Cin * 2};

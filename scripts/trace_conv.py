@@ -16,7 +16,7 @@ def main():
     eng = IFNetEngine(synth_ifnet_state(0), "cuda", "fp32")
     cases = {"block0.res": (192, 192, 17, 30, 1, True), "block4.res": (32, 32, 272, 480, 1, True),
              "block4.conv0a": (64, 16, 1088, 1920, 2, False), "block2.res": (96, 96, 68, 120, 1, True),
-             "block3.res": (64, 64, 136, 240, 1, True), "gridnet64": (64, 64, 544, 960, 1, True)}
+             "block3.res": (64, 64, 136, 240, 1, True), "block4.res.x2": (32, 32, 544, 480, 1, True), "encode.cnn1": (16, 16, 544, 960, 1, True), "gridnet64": (64, 64, 544, 960, 1, True)}
     names = sys.argv[1:] or list(cases)
     trace = torch.zeros(4096, dtype=torch.int64, device="cuda")
     for name in names:
@@ -45,16 +45,15 @@ def main():
         print(f"== {name}: start 0, after setup+griddep {rel(t[4091])}, end {rel(t[4092])} (cycles; ~1.9 GHz)")
         for li in range(nl):
             base = li * 256
-            rows = []
-            for it in range(48):
-                if t[base + it * 4 + 1] == 0:
+            print(f" layer {li}: per tile of CTA 0: K iteration 0/1 (prod_prewait, prod_issued, mma_full, mma_issued) | "
+                  f"epilogue group 0 (acc_full, drained) | group 1")
+            for tl in range(10):
+                b = base + tl * 16
+                if t[b + 1] == 0:
                     break
-                rows.append((it, rel(t[base + it * 4]), rel(t[base + it * 4 + 1]), rel(t[base + it * 4 + 2]), rel(t[base + it * 4 + 3])))
-            print(f" layer {li}: (it, prod_prewait, prod_issued, mma_full, mma_committed)")
-            for r in rows:
-                print("   ", r)
-            print(f"   epi: acc_full {rel(t[base + 200])} stores_done {rel(t[base + 201])} barrier_in {rel(t[base + 202])} barrier_out {rel(t[base + 203])}")
-            print(f"   epi detail (ld0 done, chunk0 stored, ld1 done, chunk1 stored): {[rel(t[base + 204 + i]) for i in range(4)]}")
+                print("   ", tl, [rel(t[b + k]) for k in range(4)], [rel(t[b + 4 + k]) for k in range(4)],
+                      "|", [rel(t[b + 8]), rel(t[b + 9])], "|", [rel(t[b + 10]), rel(t[b + 11])])
+            print(f"   barrier_in {rel(t[base + 202])} barrier_out {rel(t[base + 203])}")
 
 
 if __name__ == "__main__":

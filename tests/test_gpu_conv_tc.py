@@ -32,6 +32,9 @@ def _lrelu(x):
     (64, 16, 40, 56, 2, False),      # stride 2 (rank-5 parity view)
     (48, 96, 32, 64, 2, False),
     (16, 32, 68, 120, 2, False),
+    (32, 64, 33, 50, 1, False),      # packed halo mode (2 pixels per 128-byte line), ragged in both directions
+    (16, 16, 37, 52, 1, True),       # packed halo mode (4 pixels per line), residual
+    (32, 32, 21, 31, 1, True),       # odd width: falls back to the unpacked halo mode
 ])
 def test_conv3x3_tc_vs_torch(cin, cout, h, w, stride, res):
     from drba_b200.ifnet import _tc_conv3x3
