@@ -8,7 +8,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdrba_b200.so")
+# DRBA_B200_LIB: load another build of the same C ABI (A/B timing of kernel variants on one box)
+SO_PATH = os.environ.get("DRBA_B200_LIB") or os.path.join(_HERE, "libdrba_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _c = ctypes

@@ -78,6 +78,7 @@ struct alignas(64) LayerDev {
     int a_base, a_stride;   // byte offset of the activation ring and bytes per stage
     int halo_bo;            // experiment: write the descriptor's base_offset field
     int pack;               // packed halo mode: pixels per 128-byte line (2 or 4), else 1
+    int staged;             // epilogue moves residual / result through the per-warp staging tile
     int ntile, nsplits, cout_pad, cout;
     int swz_bytes;          // 32 / 64 / 128
     int b_sub;              // bytes of one weight tile (padded to the swizzle period)
@@ -227,6 +228,14 @@ __device__ __forceinline__ void issue_halo_packed(uint32_t tmem_d, uint64_t da0,
     }
 }
 
+// exact GELU (nn.GELU default); out of line: erff inlined 16x per site bloats every instantiation
+__device__ __noinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// epilogue staging tile of one warp: 32 pixel rows x 64 bytes; piece k (16 bytes) of row r sits at k ^ (r / 2 % 4),
+// conflict-free both for "lane = row" and for "four lanes per row" accesses
+constexpr int kStagingBytes = 2048;
+__device__ __forceinline__ int stg_slot(int r, int k) { return r * 4 + (k ^ ((r >> 1) & 3)); }
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile("{\n\t.reg .pred p;\n\t"
@@ -247,11 +256,20 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
 }
 
 
+// clock64 pipeline trace of CTA 0 (scripts/trace_conv.py): compiled in only with -DDRBA_TC_TRACE=1 -- even the
+// never-taken branches cost the producer / MMA warps 10-15 % on TMA-issue-bound layers
+#if DRBA_TC_TRACE
 #define TC_TRACE(slot) do { if (trace && blockIdx.x == 0) trace[(slot)] = clock64(); } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#endif
 
 // FULL = false: the IFNet / GMFlow feature set (one output, one residual, act none / LeakyReLU / ReLU / GELU);
 // FULL = true adds the GMFSS epilogue (second residual, up to three outputs, PReLU variants) at a higher register cost
-template <bool FULL>
+// STAGED selects the plain epilogue's data path (one instantiation carries only one of them: the kernel's code size
+// is felt by the issue-bound producer / MMA warps): true = through the per-warp staging tile (wide rows, many tiles
+// per SM), false = one lane per pixel row (latency-bound streaming layers)
+template <bool FULL, bool STAGED>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ Program prog)
 {
@@ -498,6 +516,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             const uint32_t group = (uint32_t)(warp - 2) >> 2;
             const int q = warp & 3;
             const int row = q * 32 + lane;
+            uint4* stg = reinterpret_cast<uint4*>(smem_raw + (smem - smem_u32(smem_raw)) + kStages * kStageBytes + (warp - 2) * kStagingBytes);
             const int row_w = pack > 1 ? 8 : tile_w;
             const int ry = row / row_w, rx = row - ry * row_w;
             const int OH = L.OH, OW = L.OW, cout = L.cout, cout_pad = L.cout_pad, act = L.act;
@@ -526,6 +545,152 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 const float* bias = s_bias + (has_bias ? g * cout_pad + nbase : 0);
                 const uint32_t taddr0 = tmem_base + buf * (uint32_t)kMaxNTile + ((uint32_t)(q * 32) << 16);
                 const __half* resb = (epilogue == 0) ? L.res[img] : nullptr;
+                // ---- plain epilogue (epilogue == 0): residual in and result out go through a per-warp staging tile ----
+                // One lane per pixel would touch 32 different lines per LDG.128 / STG.128 (the L1 data pipe it shares
+                // with the tensor core's operand reads became the bound); instead four lanes move one pixel's 64 bytes
+                // of a 32-channel chunk, each lane swaps through shared memory (16-byte pieces XOR-swizzled by the row
+                // pair) and reads / writes its own pixel row there.  The next chunk's residual is in flight while
+                // the current one is computed; the first one is fetched before the accumulator is waited for.
+                if (STAGED && epilogue == 0) {
+                    const int kq = lane & 3, sb = lane >> 2;
+                    const int ncc = c_hi > c_lo ? (c_hi - c_lo + 31) >> 5 : 0;
+                    const int total_chunks = (mt_hi - mt_lo) * ncc;
+                    const __half* res2b = FULL ? L.res2[img] : nullptr;
+                    __half* outb = reinterpret_cast<__half*>(L.out[img]);
+                    __half* out1b = FULL ? reinterpret_cast<__half*>(L.out1[img]) : nullptr;
+                    __half* out2b = FULL ? reinterpret_cast<__half*>(L.out2[img]) : nullptr;
+                    // element offset of this lane's pixel of M tile mt (channel nbase), -1 outside the image
+                    auto pix_off = [&](int mt) -> int {
+                        const int oy = oy_s + mt * mt_dy, ox = ox_s + mt * mt_dx;
+                        if (oy >= OH || ox >= OW) return -1;
+                        const size_t pix = os == 1 ? (size_t)oy * OW + ox
+                                                   : (size_t)(oy * os + (g >> 1)) * (OW * os) + (ox * os + (g & 1));
+                        return (int)(pix * cstride) + nbase;
+                    };
+                    uint4 rnext[4];
+                    if (resb && total_chunks > 0 && !(dbg & 16)) {
+                        const int mo = pix_off(mt_lo);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int o = __shfl_sync(0xffffffffu, mo, sb + 8 * i);
+                            if (o >= 0 && c_lo + kq * 8 < c_hi) rnext[i] = *reinterpret_cast<const uint4*>(resb + o + c_lo + kq * 8);
+                        }
+                    }
+                    mbar_wait(&acc_full[buf], use & 1u);
+                    tc_fence_after();
+                    if (tl < 10 && q == 2 && lane == 0) TC_TRACE(li * 256 + tl * 16 + 8 + group * 2);
+                    int mt = mt_lo, c0 = c_lo;
+                    for (int n = 0; n < total_chunks; ++n) {
+                        const int myoff = pix_off(mt);
+                        int offs[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) offs[i] = __shfl_sync(0xffffffffu, myoff, sb + 8 * i);
+                        const uint32_t taddr = taddr0 + (uint32_t)(mt * ntile);
+                        uint32_t rr[32];
+                        tc_ld16_nowait(taddr + c0, rr);
+                        if (c0 + 16 < c_hi) tc_ld16_nowait(taddr + c0 + 16, rr + 16);
+                        // next chunk of this group
+                        int mt2 = mt, c02 = c0 + 32;
+                        if (c02 >= c_hi) { c02 = c_lo; ++mt2; }
+                        const bool use_res = resb && !(dbg & 16);
+                        if (use_res) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (c0 + kq * 8 < c_hi) stg[stg_slot(sb + 8 * i, kq)] = rnext[i];
+                            __syncwarp();
+                            if (n + 1 < total_chunks) {
+                                const int mo = mt2 == mt ? myoff : pix_off(mt2);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int o = __shfl_sync(0xffffffffu, mo, sb + 8 * i);
+                                    if (o >= 0 && c02 + kq * 8 < c_hi) rnext[i] = *reinterpret_cast<const uint4*>(resb + o + c02 + kq * 8);
+                                }
+                            }
+                        }
+                        tc_ld_wait();
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int c = c0 + hh * 16;
+                            if (c >= c_hi) continue;
+                            float v[16];
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b4 = has_bias ? *reinterpret_cast<const float4*>(bias + c + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                v[i] = __uint_as_float(rr[hh * 16 + i]) + b4.x;
+                                v[i + 1] = __uint_as_float(rr[hh * 16 + i + 1]) + b4.y;
+                                v[i + 2] = __uint_as_float(rr[hh * 16 + i + 2]) + b4.z;
+                                v[i + 3] = __uint_as_float(rr[hh * 16 + i + 3]) + b4.w;
+                            }
+                            if (use_res) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const uint4 rv = stg[stg_slot(lane, hh * 2 + h)];
+                                    const __half2* hp = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const float2 f = __half22float2(hp[k]);
+                                        v[h * 8 + k * 2] += f.x; v[h * 8 + k * 2 + 1] += f.y;
+                                    }
+                                }
+                            }
+                            if (FULL && res2b && myoff >= 0) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const uint4 rv = reinterpret_cast<const uint4*>(res2b + myoff + c)[h];
+                                    const __half2* hp = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const float2 f = __half22float2(hp[k]);
+                                        v[h * 8 + k * 2] += f.x; v[h * 8 + k * 2 + 1] += f.y;
+                                    }
+                                }
+                            }
+                            // up to three outputs of the same pre-activation value, each with its own activation
+#pragma unroll
+                            for (int oi = 0; oi < (FULL ? 3 : 1); ++oi) {
+                                __half* ob = oi == 0 ? outb : (oi == 1 ? out1b : out2b);
+                                if (!ob) continue;
+                                const int a = oi == 0 ? act : (oi == 1 ? act1 : act2);
+                                const float sl = a == 1 ? 0.2f : (a == 3 ? 0.0f : (oi == 0 ? slope0 : (oi == 1 ? slope1 : slope2)));
+                                float w[16];
+                                if (a == 0) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) w[i] = v[i];
+                                } else if (FULL && a == 2) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) w[i] = v[i] > 0.0f ? v[i] : s_slope[nbase + c + i] * v[i];
+                                } else if (a == 5) {      // exact GELU (nn.GELU default)
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) w[i] = gelu_exact(v[i]);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) w[i] = v[i] > 0.0f ? v[i] : sl * v[i];
+                                }
+                                uint4 o[2];
+                                __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) oh[k] = __floats2half2_rn(w[2 * k], w[2 * k + 1]);
+                                if (oi == 0) {
+                                    stg[stg_slot(lane, hh * 2)] = o[0];
+                                    stg[stg_slot(lane, hh * 2 + 1)] = o[1];
+                                } else if (myoff >= 0 && nbase + c < cout) {
+                                    uint4* o4 = reinterpret_cast<uint4*>(ob + myoff + c);
+                                    o4[0] = o[0]; o4[1] = o[1];
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        {
+                            const int cc = c0 + kq * 8;          // this lane's 8 columns; whole 16-column groups beyond cout stay unwritten
+                            const bool wr = cc < c_hi && nbase + (cc & ~15) < cout && !(dbg & 8);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (wr && offs[i] >= 0) *reinterpret_cast<uint4*>(outb + offs[i] + cc) = stg[stg_slot(sb + 8 * i, kq)];
+                        }
+                        __syncwarp();
+                        mt = mt2; c0 = c02;
+                    }
+                } else {
                 // the residual does not depend on the accumulator: fetch (up to) 32 channels of the first M tile before waiting
                 uint4 rpre[4];
                 {
@@ -544,7 +709,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                     const int oy = oy_s + mt * mt_dy, ox = ox_s + mt * mt_dx;
                     const bool valid = oy < OH && ox < OW;
                     const uint32_t taddr = taddr0 + (uint32_t)(mt * ntile);
-                    if (epilogue == 0) {
+                    if (!STAGED && epilogue == 0) {
                         const size_t pix = os == 1 ? (size_t)oy * OW + ox
                                                    : (size_t)(oy * os + (g >> 1)) * (OW * os) + (ox * os + (g & 1));
                         __half* out = reinterpret_cast<__half*>(L.out[img]) + pix * cstride + nbase;
@@ -613,7 +778,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                                         for (int i = 0; i < 16; ++i) w[i] = v[i] > 0.0f ? v[i] : s_slope[nbase + c + i] * v[i];
                                     } else if (a == 5) {      // exact GELU (nn.GELU default)
 #pragma unroll
-                                        for (int i = 0; i < 16; ++i) w[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
+                                        for (int i = 0; i < 16; ++i) w[i] = gelu_exact(v[i]);
                                     } else {
 #pragma unroll
                                         for (int i = 0; i < 16; ++i) w[i] = v[i] > 0.0f ? v[i] : sl * v[i];
@@ -654,6 +819,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                             }
                         }
                     }
+                }
                 }
                 if (tl < 10 && q == 2 && lane == 0) TC_TRACE(li * 256 + tl * 16 + 9 + group * 2);
                 // accumulator drained: hand the buffer back to the MMA warp
@@ -870,6 +1036,13 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     L.halo = halo ? 1 : 0;
     L.halo_bo = env_halo_bo;
     L.pack = halo ? pack : 1;
+    {
+        static int env_staged = -1;
+        if (env_staged < 0) { const char* e = getenv("DRBA_TC_STAGED"); env_staged = e ? atoi(e) : 1; }
+        // staging pays where rows are wide or the residual would otherwise be fetched chunk by chunk; latency-bound
+        // streaming layers (one or two tiles per SM) keep the direct per-pixel path
+        L.staged = (env_staged == 2 || (env_staged == 1 && resident && d.epilogue == 0)) ? 1 : 0;
+    }
     L.KI = halo ? L.kchunks : T * L.kchunks;
     if (resident) {
         L.a_base = (int)w_bytes;
@@ -955,10 +1128,12 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
     int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
     if (env_grid > 0 && env_grid < grid) grid = env_grid;
     static bool attr_set = false;
-    const size_t smem = (size_t)kBRegion + (size_t)kStages * kABytesMax + 1024;   // == kStages * kStageBytes + 1024
+    const size_t smem = (size_t)kBRegion + (size_t)kStages * kABytesMax + 1024 + 8 * kStagingBytes;   // ring + alignment + epilogue staging
     if (!attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
     bool full = false;
@@ -978,7 +1153,13 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = env_pdl ? 1 : 0;
-    const cudaError_t le = full ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, prog) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, prog);
+    // staged epilogue when most plain layers of the program keep their weights resident (halo layers: many tiles per SM)
+    int n_staged = 0, n_plain = 0;
+    for (int i = 0; i < nlayers; ++i)
+        if (layers[i].epilogue == 0) { ++n_plain; n_staged += prog.L[i].staged; }
+    const bool staged = n_plain > 0 && 2 * n_staged >= n_plain;
+    const cudaError_t le = full ? (staged ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, prog) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, prog))
+                                : (staged ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, prog) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, prog));
     if (le != cudaSuccess) return (int)le;
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
