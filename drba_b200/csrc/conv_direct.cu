@@ -112,6 +112,76 @@ direct_conv_kernel(const DirectConvParams p)
     }
 }
 
+
+// ---- Head.cnn0 of the tensor-core engine (IFNet_HDv3.py:31: Conv2d(3, 16, 3, 2, 1) + LeakyReLU) ------------------
+// Planar fp32 image in, NHWC fp16 out.  The generic kernel above stages 8-channel patches and 16x16 tiles for a
+// layer that has 27 inputs per output: 97 us at 1080p against ~42 MB of traffic.  Here one thread owns two
+// vertically adjacent outputs (weights are read once for both, broadcast from shared memory), a warp covers 32
+// consecutive columns so every image row segment is read as whole lines.  Same fmaf order as the generic kernel
+// (tap-major, input channel inner), so the results are identical.
+__global__ void __launch_bounds__(256)
+head_conv0_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                  __half* __restrict__ out, int H, int W, long long in_sn, long long in_sc, long long in_sy,
+                  int OH, int OW, long long out_sn, long long out_sy)
+{
+    __shared__ __align__(16) float wsm[27 * 16];
+    __shared__ float bsm[16];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int e = tid; e < 27 * 16; e += 256) wsm[e] = w[e];
+    if (tid < 16) bsm[tid] = bias ? bias[tid] : 0.0f;
+    __syncthreads();
+    const int ox = blockIdx.x * 32 + threadIdx.x;
+    const int oy = (blockIdx.y * 8 + threadIdx.y) * 2;
+    if (ox >= OW || oy >= OH) return;
+    const float* inn = in + (long long)blockIdx.z * in_sn;
+    float acc[2][16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { acc[0][k] = 0.0f; acc[1][k] = 0.0f; }
+    // input rows 2*oy - 1 .. 2*oy + 3: output oy uses rows 0..2 of them, output oy + 1 rows 2..4
+    float v[5][3][3];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const int iy = 2 * oy - 1 + r;
+        const bool yok = iy >= 0 && iy < H;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                v[r][ci][kx] = (yok && ix >= 0 && ix < W) ? inn[ci * in_sc + iy * in_sy + ix] : 0.0f;
+            }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+            const float4* w4 = reinterpret_cast<const float4*>(wsm + (t * 3 + ci) * 16);
+            const float a = v[t / 3][ci][t % 3], b = v[t / 3 + 2][ci][t % 3];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                const float4 ww = w4[k4];
+                acc[0][k4 * 4 + 0] = fmaf(a, ww.x, acc[0][k4 * 4 + 0]); acc[1][k4 * 4 + 0] = fmaf(b, ww.x, acc[1][k4 * 4 + 0]);
+                acc[0][k4 * 4 + 1] = fmaf(a, ww.y, acc[0][k4 * 4 + 1]); acc[1][k4 * 4 + 1] = fmaf(b, ww.y, acc[1][k4 * 4 + 1]);
+                acc[0][k4 * 4 + 2] = fmaf(a, ww.z, acc[0][k4 * 4 + 2]); acc[1][k4 * 4 + 2] = fmaf(b, ww.z, acc[1][k4 * 4 + 2]);
+                acc[0][k4 * 4 + 3] = fmaf(a, ww.w, acc[0][k4 * 4 + 3]); acc[1][k4 * 4 + 3] = fmaf(b, ww.w, acc[1][k4 * 4 + 3]);
+            }
+        }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (oy + j >= OH) break;
+        uint4 o[2];
+        __half* oh = reinterpret_cast<__half*>(o);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float x = acc[j][k] + bsm[k];
+            x = x > 0.0f ? x : 0.2f * x;
+            oh[k] = __float2half_rn(x);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + (long long)blockIdx.z * out_sn + (long long)(oy + j) * out_sy + (long long)ox * 16);
+        dst[0] = o[0]; dst[1] = o[1];
+    }
+}
+
 }  // namespace drba
 
 using namespace drba;
@@ -130,6 +200,21 @@ int drba_conv2d_direct_f32(const float* in, const float* w, const float* bias, c
     if (out_dtype != DRBA_F32 && out_dtype != DRBA_F16) return DRBA_E_ARG;
     if ((size_t)N * OH * OW == 0) return DRBA_OK;
     if (!in || !w || !out) return DRBA_E_ARG;
+    {
+        // Head.cnn0 fast path: 3 -> 16 channels, 3x3 stride 2 pad 1, LeakyReLU, planar fp32 -> NHWC fp16
+        bool canon = Cin == 3 && Cout == 16 && T == 9 && S == 2 && OS == 1 && PY == 0 && PX == 0 && act == 1 && !res &&
+                     out_dtype == DRBA_F16 && in_strides[3] == 1 && out_strides[1] == 1 && out_strides[3] == 16 &&
+                     out_strides[2] % 8 == 0 && out_strides[0] % 8 == 0 && aligned16(out) && N <= 65535;
+        for (int t = 0; canon && t < 9; ++t) canon = dy[t] == t / 3 - 1 && dx[t] == t % 3 - 1;
+        if (canon) { const char* e = getenv("DRBA_DIRECT_GENERIC"); canon = !(e && e[0] == '1'); }   // tests: force the generic kernel
+        if (canon) {
+            dim3 grid((OW + 31) / 32, (OH + 15) / 16, N);
+            head_conv0_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(in, w, bias, (__half*)out, H, W, in_strides[0], in_strides[1],
+                                                                           in_strides[2], OH, OW, out_strides[0], out_strides[2]);
+            DRBA_RETURN_IF_LAUNCH_FAILED();
+            return DRBA_OK;
+        }
+    }
     DirectConvParams p;
     p.in = in; p.w = w; p.bias = bias; p.res = (const float*)res; p.out = (float*)out; p.out_half = out_dtype == DRBA_F16;
     p.N = N; p.Cin = Cin; p.H = H; p.W = W;

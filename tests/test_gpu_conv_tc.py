@@ -154,3 +154,24 @@ def test_conv_program_chain_vs_torch(c, h, w, nimg):
         err = (got - ref).abs()
         tol = 6e-3 + 4e-3 * ref.abs()      # 4 layers of fp16 re-rounding
         assert (err <= tol).all(), f"image {k}: max err {err.max().item():.4g}"
+
+
+@pytest.mark.parametrize("h,w", [(64, 96), (70, 50), (34, 66)])
+def test_head_cnn0_fast_path_matches_generic_kernel(monkeypatch, h, w):
+    """Head.cnn0 (IFNet_HDv3.py:31) has its own kernel in the tensor-core engine; it must give exactly what the
+    generic direct convolution gives, and both must match torch."""
+    eng = _engine()
+    g = torch.Generator(device="cpu").manual_seed(h * 7 + w)
+    img = torch.rand((1, 3, h, w), generator=g).cuda()
+    layer = eng.direct["encode.cnn0"]
+    h2, w2 = (h + 1) // 2, (w + 1) // 2
+    outs = []
+    for generic in ("1", "0"):
+        monkeypatch.setenv("DRBA_DIRECT_GENERIC", generic)
+        out = torch.full((h2, w2, 16), float("nan"), dtype=torch.float16, device="cuda")
+        eng._conv_direct(layer, img.data_ptr(), h, w, (3 * h * w, h * w, w, 1), out, h2, w2, (h2 * w2 * 16, 1, w2 * 16, 16))
+        torch.cuda.synchronize()
+        outs.append(out.view(torch.int16).cpu().numpy())
+    np.testing.assert_array_equal(outs[0], outs[1])
+    got = torch.from_numpy(outs[1]).view(torch.float16).float()
+    assert torch.isfinite(got).all() and got.abs().max() > 0
