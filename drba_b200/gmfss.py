@@ -19,6 +19,7 @@ import os
 import torch
 
 from . import _lib
+from ._graphs import WindowGraphs
 from ._torch_util import Workspace, ptr, require_cuda, stream_ptr
 from .drm import calc_drm_gmfss
 from .gmfss_nets import FeatureNet, GridNet, MetricNet, pack_planes
@@ -161,7 +162,7 @@ class Model:
 
 
 class GMFSS:
-    def __init__(self, weights=r'weights/train_log_gmfss', scale=1.0, device=None, state=None, flow_estimator=None):
+    def __init__(self, weights=r'weights/train_log_gmfss', scale=1.0, device=None, state=None, flow_estimator=None, graphs=None):
         if device is None:
             device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         device = torch.device(device)
@@ -174,6 +175,11 @@ class GMFSS:
         self.model = Model(state, device, flow_estimator)
         self.scale = scale
         self.pad_size = 64
+        # graphs: every distinct window shape is captured into a CUDA graph once and replayed (_graphs.py).  Default: on
+        # with the native GMFlow; off with an injected flow_estimator (arbitrary Python, may synchronise)
+        if graphs is None:
+            graphs = flow_estimator is None
+        self._windows = WindowGraphs(self._drba_eager, device) if graphs else None
 
     @torch.inference_mode()
     def inference_ts(self, I0, I1, ts):
@@ -192,6 +198,11 @@ class GMFSS:
     @torch.inference_mode()
     def inference_ts_drba(self, I0, I1, I2, ts, reuse=None, linear=False):
         """models/gmfss.py:35-73."""
+        if self._windows is not None:
+            return self._windows(I0, I1, I2, ts, reuse, linear)
+        return self._drba_eager(I0, I1, I2, ts, reuse, linear)
+
+    def _drba_eager(self, I0, I1, I2, ts, reuse=None, linear=False):
         reuseI1I0 = self.model.reuse(I1, I0, self.scale) if reuse is None else reuse
         reuseI1I2 = self.model.reuse(I1, I2, self.scale)
         flow10, metric10 = reuseI1I0[0], reuseI1I0[2]

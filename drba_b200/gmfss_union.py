@@ -13,6 +13,7 @@ import torch
 
 from . import _lib
 from .drm import calc_drm_gmfss, calc_drm_rife_auxiliary
+from ._graphs import WindowGraphs
 from .gmfss import Model
 from .ifnet import IFNetEngine
 from .ops import resize_bilinear
@@ -40,7 +41,7 @@ def load_union_rife_state(weights_dir):
 
 class GMFSS_UNION:
     def __init__(self, weights='weights/train_log_gmfss_union', scale=1.0, device=None, state=None, rife_state=None,
-                 flow_estimator=None, precision="fp16"):
+                 flow_estimator=None, precision="fp16", graphs=None):
         if device is None:
             device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         device = torch.device(device)
@@ -56,6 +57,11 @@ class GMFSS_UNION:
         self.scale = scale
         self.scale_list = [16 / self.scale, 8 / self.scale, 4 / self.scale, 2 / self.scale, 1 / self.scale]
         self.pad_size = 128
+        # graphs: every distinct window shape is captured into a CUDA graph once and replayed (_graphs.py).  Default: on
+        # with the native GMFlow; off with an injected flow_estimator (arbitrary Python, may synchronise)
+        if graphs is None:
+            graphs = flow_estimator is None
+        self._windows = WindowGraphs(self._drba_eager, device) if graphs else None
 
     @torch.inference_mode()
     def inference_ts(self, I0, I1, ts):
@@ -77,6 +83,11 @@ class GMFSS_UNION:
     @torch.inference_mode()
     def inference_ts_drba(self, I0, I1, I2, ts, reuse=None, linear=False):
         """models/gmfss_union.py:45-100."""
+        if self._windows is not None:
+            return self._windows(I0, I1, I2, ts, reuse, linear)
+        return self._drba_eager(I0, I1, I2, ts, reuse, linear)
+
+    def _drba_eager(self, I0, I1, I2, ts, reuse=None, linear=False):
         reuseI1I0 = self.model.reuse(I1, I0, self.scale) if reuse is None else reuse
         reuseI1I2 = self.model.reuse(I1, I2, self.scale)
         flow10, metric10 = reuseI1I0[0], reuseI1I0[2]

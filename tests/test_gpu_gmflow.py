@@ -158,3 +158,81 @@ def test_gmfss_window_with_native_gmflow(gg=None):
         mse = float(np.mean((y.cpu().numpy().astype(np.float64) - want) ** 2))
         p = 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
         assert p >= 36.0, f"{key}: PSNR {p:.1f} dB"
+
+
+@pytest.mark.parametrize("h,w,k,C", [(16, 24, 2, 128), (34, 60, 2, 128), (18, 30, 1, 64), (20, 28, 2, 64)])
+@pytest.mark.parametrize("shifted", [0, 1])
+@pytest.mark.parametrize("transposed", [0, 1])
+def test_window_pack_matches_split_window_semantics(h, w, k, C, shifted, transposed):
+    """Window packing (transformer.py:20-45 roll + utils.py split_feature) incl. the transposed V^T form: exact
+    copy semantics, padding rows untouched."""
+    from drba_b200._lib import lib, check
+    from drba_b200._torch_util import ptr, stream_ptr
+    L = lib()
+    g = torch.Generator(device="cuda").manual_seed(h * 100 + w + k)
+    B = 2
+    x = torch.randn((B, h, w, C), device="cuda", generator=g).half()
+    wh, ww = h // k, w // k
+    Lw = wh * ww
+    Lp = (Lw + 15) // 16 * 16
+    shape = (B * k * k, C, Lp) if transposed else (B * k * k, Lp, C)
+    out = torch.full(shape, -7.0, device="cuda", dtype=torch.float16)
+    check(L.drba_gmflow_window_pack(ptr(x), ptr(out), B, h, w, C, k, shifted, Lp, transposed, stream_ptr("cuda")), "window_pack")
+    torch.cuda.synchronize()
+    xr = torch.roll(x, shifts=(-(wh // 2), -(ww // 2)), dims=(1, 2)) if shifted else x
+    ref = xr.view(B, k, wh, k, ww, C).permute(0, 1, 3, 2, 4, 5).reshape(B * k * k, Lw, C)
+    if transposed:
+        assert torch.equal(out[:, :, :Lw], ref.transpose(1, 2))
+        assert (out[:, :, Lw:] == -7.0).all()
+    else:
+        assert torch.equal(out[:, :Lw], ref)
+        assert (out[:, Lw:] == -7.0).all()
+
+
+@pytest.mark.parametrize("union", [False, True])
+def test_graphed_windows_match_eager_windows(union):
+    """CUDA-graph replay of DRBA windows (drba_b200/_graphs.py) against the eager path: three chained windows with the
+    alternating timestamp patterns and the `reuse` hand-over (models/gmfss.py:35-73, models/gmfss_union.py:45-100)."""
+    from drba_b200.weights import synth_gmfss_state, synth_ifnet_state
+    state = synth_gmfss_state(0, union=union)
+    state["flownet"] = _synth_state(1)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    H, W = (256, 384) if union else (128, 192)
+    base = torch.rand((1, 3, H // 8, W // 8), generator=g)
+    frames = [torch.nn.functional.interpolate(torch.roll(base, shifts=(i, 2 * i), dims=(2, 3)), size=(H, W), mode="bilinear",
+                                              align_corners=False).cuda().contiguous() for i in range(5)]
+
+    def build(graphs):
+        if union:
+            from drba_b200.gmfss_union import GMFSS_UNION
+            return GMFSS_UNION(state=state, rife_state=synth_ifnet_state(0), device="cuda", graphs=graphs)
+        from drba_b200.gmfss import GMFSS
+        return GMFSS(state=state, device="cuda", graphs=graphs)
+
+    results = []
+    for graphs in (False, False, True):
+        m = build(graphs)
+        assert (m._windows is not None) == graphs
+        reuse, outs = None, []
+        for k, ts in enumerate(([0.6, 1.0, 1.4], [0.8, 1.2], [0.6, 1.0, 1.4])):
+            o, reuse = m.inference_ts_drba(frames[k], frames[k + 1], frames[k + 2], np.array(ts), reuse, True)
+            assert len(o) == len(ts)
+            if 1.0 in ts:
+                assert o[1] is frames[k + 1]
+            outs.append([x.clone() for x in o])
+        results.append(outs)
+
+    def dist(ra, rb):
+        mean = max((a - b).abs().mean().item() for wa, wb in zip(ra, rb) for a, b in zip(wa, wb))
+        peak = max((a - b).abs().max().item() for wa, wb in zip(ra, rb) for a, b in zip(wa, wb))
+        return mean, peak
+
+    # DRM accumulates with floating-point atomics, so two eager runs already differ in the last bits and the random
+    # stand-in weights amplify that (measured: mean 1e-4, peak 7e-3); a stale buffer or a wrong `reuse` hand-over in
+    # the replayed graphs would show as a different frame (mean > 1e-2)
+    for other in (results[1], results[2]):
+        mean, peak = dist(results[0], other)
+        assert mean <= 1e-3 and peak <= 5e-2, (mean, peak)
+    for w in results[2]:
+        for x in w:
+            assert torch.isfinite(x).all()
