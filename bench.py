@@ -247,7 +247,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--warmup-seconds", type=float, default=1.0,
                     help="keep running warm-up windows until this much wall time has passed (clock ramp from idle)")
@@ -350,16 +350,18 @@ def main():
     for f in frames:
         f8 = torch.nn.functional.interpolate(f, size=(H_SRC, W_SRC), mode="bilinear", align_corners=False)
         host_u8.append((f8[0].permute(1, 2, 0) * 255.0).clamp(0, 255).to(torch.uint8).contiguous().cpu().pin_memory())
-    win = [io.upload(host_u8[0]), io.upload(host_u8[1])]
+    # the new frame of a window is uploaded while the PREVIOUS window computes (one frame ahead, like the reference's
+    # reader thread): every step still moves exactly one frame in and all of its output frames out
+    win = [io.upload(host_u8[0]), io.upload(host_u8[1]), io.upload(host_u8[2])]
     reuse_e = None
 
     def e2e_window(j, reuse_e):
-        win.append(io.upload(host_u8[(j + 2) % ring]))     # the new frame of this window arrives from the host
         I0, I1, I2 = win[-3], win[-2], win[-1]
         out, reuse_e = model.inference_ts_drba(I0, I1, I2, TS_PATTERN[j % 2], reuse_e, True)
-        io.release_inputs()
+        io.release_inputs((I0, I1, I2))
         for o in out:
             io.download(o)                                  # every output frame goes back to the host
+        win.append(io.upload(host_u8[(j + 3) % ring]))     # next window's new frame: H2D + ingest overlap this window
         del win[0]
         return len(out), reuse_e
 

@@ -163,12 +163,20 @@ class FrameIO:
         self._last_slot = k
         return self._in_f[k]
 
-    def release_inputs(self):
-        """Call after the work that reads the uploaded frames has been enqueued on the current stream:
-        marks every input slot as reusable once that work completes."""
+    def release_inputs(self, frames=None):
+        """Call after the work that reads uploaded frames has been enqueued on the current stream: marks their input
+        slots as reusable once that work completes.  frames: the uploaded tensors that work reads (None = every slot).
+        Naming them lets the next frame be uploaded while the window that does not touch its slot is still running
+        (upload one window ahead: the H2D copy then overlaps the compute instead of stalling it)."""
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
-        self._in_free = [ev] * len(self._in_free)
+        if frames is None:
+            self._in_free = [ev] * len(self._in_free)
+            return
+        ptrs = {f.data_ptr() for f in frames}
+        for k, buf in enumerate(self._in_f):
+            if buf.data_ptr() in ptrs:
+                self._in_free[k] = ev
 
     def download(self, frame):
         """Enqueue egress + D2H of a float frame produced on the current stream; returns the pinned host buffer
