@@ -336,7 +336,9 @@ def main():
         ev[k + 1].record()
     barrier()
     ms = ev[0].elapsed_time(ev[K])
-    step_ms = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(K))
+    step_raw = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
+    step_ms = sorted(step_raw)
+    slow_steps = [(k, round(v, 2)) for k, v in enumerate(step_raw) if v > 3.0 * step_ms[K // 2]][:8]
     launches = _lib.KERNEL_LAUNCHES - launches0
 
     # ---- end to end through the public API with HOST buffers ------------------------------------------
@@ -458,7 +460,7 @@ def main():
                              f"{secs:.1f} s; oracle port (torch fp32 CPU convs + C splat/warp)"}
         line = {"metric": METRIC, "value": round(nout_all / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world,
                 "steps": K, "warmup": Wm, "ms_per_step": round(ms / K, 4), "higher_is_better": True,
-                "ms_per_step_median": round(step_ms[K // 2], 4), "ms_per_step_max": round(step_ms[-1], 4), "warmup_windows_run": Wm_done,
+                "ms_per_step_median": round(step_ms[K // 2], 4), "ms_per_step_max": round(step_ms[-1], 4), "slow_steps": slow_steps, "warmup_windows_run": Wm_done,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32",
                 "data": "synthetic",
                 "config": {"workload": "RIFE-4.26-heavy 1080p 24->60, scale=1.0 (BASELINE.json configs[1])",

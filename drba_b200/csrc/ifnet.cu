@@ -22,161 +22,9 @@
 //                   flow (+)= s * up(lastconv[0:4])  (IFNet_HDv3.py:91-93, :157), 32 B/px.
 //  ifnet_blend    : last flow update + final warps + sigmoid blend (IFNet_HDv3.py:156-167) in
 //                   one pass; the last block's flow/mask are never stored at full resolution.
-#include "common.cuh"
+#include "ifnet_common.cuh"
 
 namespace drba {
-
-constexpr int kIfThreads = 128;
-
-struct WarpTap {
-    int i00, i01, i10, i11;   // element offsets y*W+x, or -1 when the tap is out of range
-    float w00, w01, w10, w11;
-};
-
-// warplayer.py:8-22: border padding, align_corners=True, pixel coordinates
-__device__ __forceinline__ WarpTap warp_tap(int x, int y, float fx, float fy, int H, int W)
-{
-    WarpTap t;
-    float sx = fminf(fmaxf((float)x + fx, 0.0f), (float)(W - 1));
-    float sy = fminf(fmaxf((float)y + fy, 0.0f), (float)(H - 1));
-    const float fx0 = floorf(sx), fy0 = floorf(sy);
-    const int x0 = (int)fx0, y0 = (int)fy0;
-    const float ax = sx - fx0, ay = sy - fy0;
-    t.w00 = (1.0f - ax) * (1.0f - ay);
-    t.w01 = ax * (1.0f - ay);
-    t.w10 = (1.0f - ax) * ay;
-    t.w11 = ax * ay;
-    const bool vx1 = x0 + 1 < W, vy1 = y0 + 1 < H;
-    t.i00 = y0 * W + x0;
-    t.i01 = vx1 ? t.i00 + 1 : -1;
-    t.i10 = vy1 ? t.i00 + W : -1;
-    t.i11 = (vx1 && vy1) ? t.i00 + W + 1 : -1;
-    return t;
-}
-
-__device__ __forceinline__ float sample_plane(const float* __restrict__ src, const WarpTap& t)
-{
-    float acc = 0.0f;
-    acc += src[t.i00] * t.w00;
-    if (t.i01 >= 0) acc += src[t.i01] * t.w01;
-    if (t.i10 >= 0) acc += src[t.i10] * t.w10;
-    if (t.i11 >= 0) acc += src[t.i11] * t.w11;
-    return acc;
-}
-
-__device__ __forceinline__ void load16(const float* __restrict__ p, float* v)
-{
-    const float4* q = reinterpret_cast<const float4*>(p);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 a = q[i];
-        v[i * 4 + 0] = a.x; v[i * 4 + 1] = a.y; v[i * 4 + 2] = a.z; v[i * 4 + 3] = a.w;
-    }
-}
-__device__ __forceinline__ void load16(const __half* __restrict__ p, float* v)
-{
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const uint4 a = q[i];
-        const __half2* h = reinterpret_cast<const __half2*>(&a);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f = __half22float2(h[k]);
-            v[i * 8 + k * 2] = f.x; v[i * 8 + k * 2 + 1] = f.y;
-        }
-    }
-}
-
-// bilinear sample of a 16-channel NHWC feature map, same accumulation order as sample_plane
-template <typename FT>
-__device__ __forceinline__ void sample_feat16(const FT* __restrict__ f, const WarpTap& t, float* out)
-{
-    float v[16];
-    load16(f + (size_t)t.i00 * 16, v);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) out[c] = 0.0f + v[c] * t.w00;
-    if (t.i01 >= 0) { load16(f + (size_t)t.i01 * 16, v);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) out[c] += v[c] * t.w01; }
-    if (t.i10 >= 0) { load16(f + (size_t)t.i10 * 16, v);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) out[c] += v[c] * t.w10; }
-    if (t.i11 >= 0) { load16(f + (size_t)t.i11 * 16, v);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) out[c] += v[c] * t.w11; }
-}
-
-// ---- lastconv output access -----------------------------------------------------------
-// TMP_LAYOUT 0: ConvTranspose output, NCHW fp32 [52][h13/2][w13/2] (PixelShuffle(2) is index
-//               arithmetic here: IFNet_HDv3.py:81)
-// TMP_LAYOUT 1: pixel-shuffled NHWC fp32 [h13][w13][16] (13 used), written by the tensor-core
-//               engine's lastconv epilogue
-struct Tmp13 {
-    const float* p; int h13, w13, s;   // 13-channel map at 1/s of the full resolution
-};
-
-struct Bilin {           // F.interpolate(scale_factor=s, bilinear, align_corners=False) source taps
-    int y0, y1, x0, x1;
-    float ly, hy, lx, hx;
-};
-
-__device__ __forceinline__ Bilin bilin_up(int y, int x, const Tmp13& t)
-{
-    Bilin b;
-    const float r = 1.0f / (float)t.s;                 // ATen: ratio = 1 / scale_factor
-    float sy = r * ((float)y + 0.5f) - 0.5f, sx = r * ((float)x + 0.5f) - 0.5f;
-    if (sy < 0.0f) sy = 0.0f;
-    if (sx < 0.0f) sx = 0.0f;
-    b.y0 = (int)sy; b.x0 = (int)sx;
-    b.y1 = b.y0 + (b.y0 < t.h13 - 1 ? 1 : 0);
-    b.x1 = b.x0 + (b.x0 < t.w13 - 1 ? 1 : 0);
-    b.ly = sy - (float)b.y0; b.hy = 1.0f - b.ly;
-    b.lx = sx - (float)b.x0; b.hx = 1.0f - b.lx;
-    return b;
-}
-
-template <int TMP_LAYOUT, int C0, int NC>
-__device__ __forceinline__ void load_tmp(const Tmp13& t, int yy, int xx, float* v)
-{
-    if (TMP_LAYOUT == 0) {
-        const int h2 = t.h13 >> 1, w2 = t.w13 >> 1;
-        const size_t base = (size_t)(yy >> 1) * w2 + (xx >> 1);
-        const int sub = (yy & 1) * 2 + (xx & 1);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) v[c] = t.p[(size_t)((C0 + c) * 4 + sub) * h2 * w2 + base];
-    } else {
-        const float* q = t.p + ((size_t)yy * t.w13 + xx) * 16;
-        if (C0 % 4 == 0) {
-            const float4* q4 = reinterpret_cast<const float4*>(q + C0);
-#pragma unroll
-            for (int c4 = 0; c4 < (NC + 3) / 4; ++c4) {
-                const float4 a = q4[c4];
-                if (c4 * 4 + 0 < NC) v[c4 * 4 + 0] = a.x;
-                if (c4 * 4 + 1 < NC) v[c4 * 4 + 1] = a.y;
-                if (c4 * 4 + 2 < NC) v[c4 * 4 + 2] = a.z;
-                if (c4 * 4 + 3 < NC) v[c4 * 4 + 3] = a.w;
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) v[c] = q[C0 + c];
-        }
-    }
-}
-
-// channels [C0, C0+NC) of the x s bilinear up-sampling of the 13-channel map at (y, x)
-template <int TMP_LAYOUT, int C0, int NC>
-__device__ __forceinline__ void up_tmp(const Tmp13& t, int y, int x, float* o)
-{
-    const Bilin b = bilin_up(y, x, t);
-    float a[NC], bb[NC], c[NC], d[NC];
-    load_tmp<TMP_LAYOUT, C0, NC>(t, b.y0, b.x0, a);
-    load_tmp<TMP_LAYOUT, C0, NC>(t, b.y0, b.x1, bb);
-    load_tmp<TMP_LAYOUT, C0, NC>(t, b.y1, b.x0, c);
-    load_tmp<TMP_LAYOUT, C0, NC>(t, b.y1, b.x1, d);
-#pragma unroll
-    for (int k = 0; k < NC; ++k) o[k] = b.hy * (b.hx * a[k] + b.lx * bb[k]) + b.ly * (b.hx * c[k] + b.lx * d[k]);
-}
 
 // ---- flow state: flow (+)= s * up(tmp[0:4])  (IFNet_HDv3.py:91-93, :157) ---------------------
 template <int TMP_LAYOUT>
@@ -203,16 +51,6 @@ ifnet_flow_accum_kernel(const Tmp13 t, float* __restrict__ flow, float* __restri
 }
 
 // ---- block input assembly ---------------------------------------------------------------
-struct AssembleParams {
-    const float* img0; const float* img1;   // [3][H][W] fp32
-    const void* f0; const void* f1;         // [H][W][16] FT
-    const float* timestep; float timestep_scalar;   // [H][W] or NULL -> scalar
-    const float* flow;                      // [H][W][4] fp32 state, or NULL (first block: no warp, 39 channels)
-    Tmp13 prev;                             // previous block's lastconv output (mask/feat source)
-    void* out; int out_cstride;             // NHWC: channels allocated per pixel
-    int H, W, s, h, w;                      // full size, integer scale, h = H/s, w = W/s
-};
-
 // Mean of the (up to) 4 sampled positions in the order bilinear resampling adds them:
 // 0.5*(0.5*a + 0.5*b) + 0.5*(0.5*c + 0.5*d) == ((a + b) + (c + d)) * 0.25 exactly in fp32.
 // a0 collects positions 0,1 (top row), a1 positions 2,3 (bottom row).
@@ -345,184 +183,6 @@ ifnet_assemble_kernel(const AssembleParams p)
     store16<NHWC_HALF>(p, Y, X, role, v, n);
 }
 
-// ---- block input assembly, tensor-core engine (NHWC fp16 in / out), L1-friendly lane mapping ----------
-// The one-lane-per-pixel kernel above is bound by the L1 data stage (ncu: l1tex 68-86 %): with a lane
-// stride of 32-128 B every LDG.128 / STG.128 touches 8-32 lines.  Here adjacent lanes cover adjacent
-// bytes: a lane pair shares a pixel's 32 B of features, x-adjacent sample positions sit in adjacent
-// lanes (the 2x2 mean becomes two shuffles, same summation order as acc_pos / mean_pos), and the
-// 128 B/pixel output row is staged in shared memory and stored as full lines.  Results are bit-identical
-// to ifnet_assemble_kernel<__half, true, 1>.
-__device__ __forceinline__ void load8(const __half* __restrict__ p, float* v)
-{
-    const uint4 a = *reinterpret_cast<const uint4*>(p);
-    const __half2* h = reinterpret_cast<const __half2*>(&a);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float2 f = __half22float2(h[k]);
-        v[k * 2] = f.x; v[k * 2 + 1] = f.y;
-    }
-}
-
-__device__ __forceinline__ void sample_feat8(const __half* __restrict__ f, const WarpTap& t, float* out)
-{
-    float v0[8], v1[8], v2[8], v3[8];
-    load8(f + (size_t)t.i00 * 16, v0);
-    load8(f + (size_t)max(t.i01, 0) * 16, v1);
-    load8(f + (size_t)max(t.i10, 0) * 16, v2);
-    load8(f + (size_t)max(t.i11, 0) * 16, v3);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float a = 0.0f + v0[c] * t.w00;
-        if (t.i01 >= 0) a += v1[c] * t.w01;
-        if (t.i10 >= 0) a += v2[c] * t.w10;
-        if (t.i11 >= 0) a += v3[c] * t.w11;
-        out[c] = a;
-    }
-}
-
-__device__ __forceinline__ uint4 pack8(const float* v)
-{
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-    return o;
-}
-
-constexpr int kAsmTile = 32;   // output pixels per CTA
-
-// 16 B chunk c of tile pixel px; rotated by 2*px so that pair / quad writers and the 8-lane row readers
-// spread over the banks
-__device__ __forceinline__ int tile_slot(int px, int c) { return px * 8 + ((c + 2 * px) & 7); }
-
-template <int NP>
-__global__ void __launch_bounds__(kIfThreads)
-ifnet_assemble_v2_kernel(const AssembleParams p)
-{
-    __shared__ __align__(16) uint4 tile[kAsmTile * 8];
-    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hw = p.h * p.w;
-    const int base = blockIdx.x * kAsmTile;
-    const int off = NP == 1 ? 0 : p.s / 2 - 1;
-    const size_t HW = (size_t)p.H * p.W;
-    const float4* flow4 = reinterpret_cast<const float4*>(p.flow);
-    constexpr int PXW = NP == 1 ? 16 : 8;      // output pixels per warp pass
-
-    if (role < 2) {
-        // lane = [pixel | x position | channel half]
-        const __half* f = reinterpret_cast<const __half*>(role == 0 ? p.f0 : p.f1) + (lane & 1) * 8;
-        const int xpos = NP == 1 ? 0 : (lane >> 1) & 1;
-        const int pl = NP == 1 ? lane >> 1 : lane >> 2;
-#pragma unroll 1
-        for (int pass = 0; pass < kAsmTile / PXW; ++pass) {
-            const int px = pass * PXW + pl;
-            const int idx = min(base + px, hw - 1);
-            const int Y = idx / p.w, X = idx - Y * p.w;
-            const int x = p.s * X + off + xpos, y = p.s * Y + off;
-            float r0[8];
-            {
-                const float4 fl = flow4[(size_t)y * p.W + x];
-                const WarpTap t = warp_tap(x, y, role == 0 ? fl.x : fl.z, role == 0 ? fl.y : fl.w, p.H, p.W);
-                sample_feat8(f, t, r0);
-            }
-            if (NP == 4) {
-                float r1[8];
-                const float4 fl = flow4[(size_t)(y + 1) * p.W + x];
-                const WarpTap t = warp_tap(x, y + 1, role == 0 ? fl.x : fl.z, role == 0 ? fl.y : fl.w, p.H, p.W);
-                sample_feat8(f, t, r1);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float a0 = r0[c] + __shfl_xor_sync(0xffffffffu, r0[c], 2);
-                    const float a1 = r1[c] + __shfl_xor_sync(0xffffffffu, r1[c], 2);
-                    r0[c] = (a0 + a1) * 0.25f;
-                }
-            }
-            if (xpos == 0) tile[tile_slot(px, role * 2 + (lane & 1))] = pack8(r0);
-        }
-    } else if (role == 2) {
-        // lane = [image | pixel | x position]
-        const int sel = lane >> 4;
-        const int xpos = NP == 1 ? 0 : lane & 1;
-        const int pl = NP == 1 ? lane & 15 : (lane >> 1) & 7;
-        const float* img = sel ? p.img1 : p.img0;
-#pragma unroll 1
-        for (int pass = 0; pass < kAsmTile / PXW; ++pass) {
-            const int px = pass * PXW + pl;
-            const int idx = min(base + px, hw - 1);
-            const int Y = idx / p.w, X = idx - Y * p.w;
-            const int x = p.s * X + off + xpos, y = p.s * Y + off;
-            float r0[3];
-            {
-                const float4 fl = flow4[(size_t)y * p.W + x];
-                const WarpTap t = warp_tap(x, y, sel ? fl.z : fl.x, sel ? fl.w : fl.y, p.H, p.W);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) r0[c] = sample_plane(img + (size_t)c * HW, t);
-            }
-            if (NP == 4) {
-                float r1[3];
-                const float4 fl = flow4[(size_t)(y + 1) * p.W + x];
-                const WarpTap t = warp_tap(x, y + 1, sel ? fl.z : fl.x, sel ? fl.w : fl.y, p.H, p.W);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) r1[c] = sample_plane(img + (size_t)c * HW, t);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float a0 = r0[c] + __shfl_xor_sync(0xffffffffu, r0[c], 1);
-                    const float a1 = r1[c] + __shfl_xor_sync(0xffffffffu, r1[c], 1);
-                    r0[c] = (a0 + a1) * 0.25f;
-                }
-            }
-            if (xpos == 0) {
-                __half* dst = reinterpret_cast<__half*>(&tile[tile_slot(px, 4)]);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) dst[sel * 3 + c] = __float2half_rn(r0[c]);
-                if (sel) *reinterpret_cast<uint32_t*>(dst + 6) = 0u;
-                else tile[tile_slot(px, 5)] = make_uint4(0u, 0u, 0u, 0u);
-            }
-        }
-    } else {
-        // lane = [pixel | sample position]; timestep, mask, feat (x s_prev up-sampling of the previous
-        // lastconv output) and flow / s
-        constexpr int PXM = NP == 1 ? 32 : 8;
-        const int K = NP == 1 ? 0 : lane & 3;
-        const int pl = NP == 1 ? lane : lane >> 2;
-        const float inv = 1.0f / (float)p.s;   // IFNet_HDv3.py:87: interpolate(flow) * 1. / scale
-#pragma unroll 1
-        for (int pass = 0; pass < kAsmTile / PXM; ++pass) {
-            const int px = pass * PXM + pl;
-            const int idx = min(base + px, hw - 1);
-            const int Y = idx / p.w, X = idx - Y * p.w;
-            const int x = p.s * X + off + (K & 1), y = p.s * Y + off + (K >> 1);
-            float v[16];
-            const float4 fl = flow4[(size_t)y * p.W + x];
-            v[0] = p.timestep ? p.timestep[(size_t)y * p.W + x] : p.timestep_scalar;
-            up_tmp<1, 4, 9>(p.prev, y, x, v + 1);
-            v[10] = fl.x; v[11] = fl.y; v[12] = fl.z; v[13] = fl.w;
-            if (NP == 4) {
-#pragma unroll
-                for (int c = 0; c < 14; ++c) {
-                    const float a = v[c] + __shfl_xor_sync(0xffffffffu, v[c], 1);
-                    v[c] = (a + __shfl_xor_sync(0xffffffffu, a, 2)) * 0.25f;
-                }
-            }
-#pragma unroll
-            for (int c = 10; c < 14; ++c) v[c] = v[c] * 1.0f * inv;
-            v[14] = 0.0f; v[15] = 0.0f;
-            if (K == 0) {
-                tile[tile_slot(px, 6)] = pack8(v);
-                tile[tile_slot(px, 7)] = pack8(v + 8);
-            }
-        }
-    }
-    __syncthreads();
-    uint4* out4 = reinterpret_cast<uint4*>(p.out);
-#pragma unroll
-    for (int k = 0; k < kAsmTile * 8 / kIfThreads; ++k) {
-        const int i = threadIdx.x + k * kIfThreads;
-        const int px = i >> 3, c = i & 7;
-        if (base + px < hw) out4[(size_t)(base + px) * 8 + c] = tile[tile_slot(px, c)];
-    }
-}
-
 // IFNet_HDv3.py:156-167: last flow update, warp both images, blend with sigmoid(mask)
 template <int TMP_LAYOUT>
 __global__ void __launch_bounds__(kIfThreads)
@@ -597,9 +257,7 @@ int drba_ifnet_assemble(const float* img0, const float* img1, const void* f0, co
     cudaStream_t st = as_stream(stream);
     const int key = (feat_dtype == DRBA_F16 ? 4 : 0) | (out_dtype == DRBA_F16 ? 2 : 0) | (tmp_layout == 1 ? 1 : 0);
     if (key == 7 && flow && out_cstride == 64 && !env_flag("DRBA_ASSEMBLE_V1")) {
-        const unsigned g2 = cdiv((size_t)p.h * p.w, kAsmTile);
-        if (s == 1) ifnet_assemble_v2_kernel<1><<<g2, kIfThreads, 0, st>>>(p);
-        else ifnet_assemble_v2_kernel<4><<<g2, kIfThreads, 0, st>>>(p);
+        launch_assemble_tc(p, st);
         DRBA_RETURN_IF_LAUNCH_FAILED();
         return DRBA_OK;
     }
