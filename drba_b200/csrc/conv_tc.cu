@@ -202,6 +202,28 @@ __device__ __forceinline__ void issue_halo(uint32_t tmem_d, uint64_t da0, uint64
     }
 }
 
+// stride-2 halo mode: the input is viewed as [H/2][2][W/2][2][C]; the four (row, column) parity planes of the
+// 17 x 9 cell neighbourhood of an 8 x 16 output tile are four boxes of one stage (sub16 apart).  Tap (ky, kx) reads
+// parity (ky != 1, kx != 1) at cell offset (ky == 0 ? -1 : 0, kx == 0 ? -1 : 0), i.e. box row / column
+// (ky != 0, kx != 0) since every box starts one cell up and left.  Rows of 8 cells are contiguous, image rows are
+// 9 cells apart (SBO).
+template <int KS>
+__device__ __forceinline__ void issue_halo_s2(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t rowb16, uint32_t sub16,
+                                              uint32_t b_tap16, uint32_t idesc, uint32_t accumulate)
+{
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        const int par = (ky != 1 ? 2 : 0) + (kx != 1 ? 1 : 0);
+        const int offr = ky != 0 ? 1 : 0, offc = kx != 0 ? 1 : 0;
+        const uint64_t da = da0 + (uint64_t)((uint32_t)par * sub16 + (uint32_t)(offr * 9 + offc) * rowb16);
+        const uint64_t db = db0 + (uint64_t)((uint32_t)tap * b_tap16);
+#pragma unroll
+        for (int k = 0; k < KS; ++k)
+            tc_mma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)(tap | k));
+    }
+}
+
 // packed halo mode (Cin = 32 or 16: P = 2 or 4 pixels share one 128-byte line; the halo box is 10 lines x 18 rows
 // for an 8P x 16 pixel tile).  M tile p holds the output pixels x = x0 + P * j + p (j = 0..7, 16 rows): for tap
 // (ty, tx) its operand rows are the input pixels x0 - P + P * j + (p + tx - 1 + P), i.e. line j + q / P of halo row
@@ -365,7 +387,8 @@ conv_tc_kernel(const __grid_constant__ Program prog)
 
         if (warp == 0) {
             // ===== activation producer: the whole warp walks the loop, one elected lane issues =====
-            const uint32_t a_bytes = (dbg & 2) ? 0u : (uint32_t)(pack > 1 ? 10 * 18 * 128 : (halo ? (16 * MT + 2) * 16 * Kc * 2 : MT * kTileM * Kc * 2));
+            const uint32_t a_bytes = (dbg & 2) ? 0u : (uint32_t)(halo == 2 ? 4 * 17 * 9 * Kc * 2 : (pack > 1 ? 10 * 18 * 128 : (halo ? (16 * MT + 2) * 16 * Kc * 2 : MT * kTileM * Kc * 2)));
+            const uint32_t s2_sub = ((uint32_t)(17 * 9 * Kc * 2) + 1023u) & ~1023u;      // stride-2 halo: one parity box
             if (li + 1 < nlayers && elect_one()) {
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].ta[0]) : "memory");
                 asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].tb) : "memory");
@@ -386,7 +409,13 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                     if (elect_one()) {
                         mbar_expect_tx(&full_bar[stage], a_bytes);
                         if (resident) mbar_arrive(&full_bar[stage]);      // stands in for the weight producer
-                        if (halo) {
+                        if (halo == 2) {
+                            if (!(dbg & 2)) {
+#pragma unroll
+                                for (int par = 0; par < 4; ++par)
+                                    tma_load_5d(a_base + stage * a_stride + (uint32_t)par * s2_sub, ta, &full_bar[stage], it * Kc, par & 1, ox0 - 1, par >> 1, oy0 - 1);
+                            }
+                        } else if (halo) {
                             // one box per K chunk: the (16*MT+2) x 16 pixel neighbourhood of the 8 x 16*MT tile
                             if (!(dbg & 2)) tma_load_5d(a_base + stage * a_stride, ta, &full_bar[stage], it * Kc, 0, pack > 1 ? ox0 / pack - 1 : ox0 - 1, 0, oy0 - 1);
                         } else {
@@ -448,6 +477,8 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             // halo mode: rows of an 8-pixel tile row are contiguous, tile rows are 16 pixels apart in the halo tile
             const uint32_t rowb16 = (uint32_t)(Kc * 2) >> 4;
             const uint64_t desc_hi_halo = (desc_hi & ~(0x3FFFull << 32)) | ((uint64_t)(16u * rowb16) << 32);
+            const uint64_t desc_hi_s2 = (desc_hi & ~(0x3FFFull << 32)) | ((uint64_t)(9u * rowb16) << 32);
+            const uint32_t s2_sub16 = (((uint32_t)(17 * 9 * Kc * 2) + 1023u) & ~1023u) >> 4;
             const uint32_t b_tap16 = (uint32_t)kchunks * b_sub16;
             const uint64_t desc_a_packed = (make_desc(0, 128) & ~(0x3FFFull << 32)) | ((uint64_t)(1280u >> 4) << 32);
             const uint32_t a_base16 = (a_base & 0x3FFFFu) >> 4, a_stride16 = a_stride >> 4;
@@ -480,6 +511,15 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                             if (ksteps == 0) {}
                             else if (pack == 2) issue_halo_packed<2>(tmem_d, da0, db0, b_tap16, ntile, idesc, accumulate);
                             else issue_halo_packed<4>(tmem_d, da0, db0, b_tap16, ntile, idesc, accumulate);
+                        } else if (halo == 2) {
+                            const uint64_t da0 = desc_hi_s2 | (uint64_t)sa16;
+                            const uint64_t db0 = desc_hi | (uint64_t)(b_tile16 + (uint32_t)it * b_sub16);
+                            switch (ksteps) {
+                                case 1: issue_halo_s2<1>(tmem_d, da0, db0, rowb16, s2_sub16, b_tap16, idesc, accumulate); break;
+                                case 2: issue_halo_s2<2>(tmem_d, da0, db0, rowb16, s2_sub16, b_tap16, idesc, accumulate); break;
+                                case 4: issue_halo_s2<4>(tmem_d, da0, db0, rowb16, s2_sub16, b_tap16, idesc, accumulate); break;
+                                default: break;
+                            }
                         } else if (halo) {
                             const uint64_t da0 = desc_hi_halo | (uint64_t)sa16;
                             const uint64_t db0 = desc_hi | (uint64_t)(b_tile16 + (uint32_t)it * b_sub16);
@@ -938,16 +978,18 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     // taps as descriptor offsets into it (8-pixel-wide tiles keep every 8-row core group contiguous; the 16-pixel
     // pitch keeps the swizzle phase identical for all groups) -- 4x fewer activation bytes than one box per tap.
     // Needs the weights resident (checked below once ntile is final).
-    static int env_halo = -1, env_halo_bo = -1, env_pack = -1;
+    static int env_halo = -1, env_halo_bo = -1, env_pack = -1, env_s2 = 1;
     if (env_halo < 0) {
         const char* e = getenv("DRBA_TC_HALO"); env_halo = e ? atoi(e) : 1;
         e = getenv("DRBA_TC_HALO_BO"); env_halo_bo = e ? atoi(e) : 0;
         e = getenv("DRBA_TC_PACK"); env_pack = e ? atoi(e) : 1;
+        e = getenv("DRBA_TC_HALO_S2"); env_s2 = e ? atoi(e) : 1;
     }
-    bool halo = env_halo && S == 1 && T == 9 && G == 1 && d.epilogue == 0 && !d.bgemm;
+    bool halo = env_halo && (S == 1 || (S == 2 && env_halo >= 1 && env_s2)) && T == 9 && G == 1 && d.epilogue == 0 && !d.bgemm;
     if (halo)
         for (int t = 0; t < 9; ++t)
             if (d.dy[t] != t / 3 - 1 || d.dx[t] != t % 3 - 1) halo = false;
+    const bool halo_s2 = halo && S == 2;      // parity-plane boxes (see issue_halo_s2)
     // M tiles per super tile: thin K steps stack M tiles so that one TMA box still carries ~16 KB
     int MT = kABytesMax / (kTileM * L.Kc * 2);
     while (MT > 1 && MT * ntile > kMaxNTile) MT >>= 1;
@@ -957,11 +999,14 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     // packed halo mode: thin inputs (16 / 32 channels) put 4 / 2 pixels on one 128-byte line, so the halo box has
     // 10 x 18 lines for an 8P x 16 pixel tile instead of 16 x (16 MT + 2) short ones (TMA time goes by the line)
     int pack = 1;
-    if (halo && env_pack && L.kchunks == 1 && L.Kc < 64 && W % (64 / L.Kc) == 0 && ntile * (64 / L.Kc) <= kMaxNTile)
+    if (halo && !halo_s2 && env_pack && L.kchunks == 1 && L.Kc < 64 && W % (64 / L.Kc) == 0 && ntile * (64 / L.Kc) <= kMaxNTile)
         pack = 64 / L.Kc;
     if (pack > 1) {
         L.tile_w = 8 * pack; L.tile_h = 16;
         best_mt = pack;
+    } else if (halo_s2) {
+        L.tile_w = 8; L.tile_h = 16;
+        best_mt = 1;
     } else if (halo) {
         L.tile_w = 8; L.tile_h = 16;
         while (MT > 1 && (OH + 16 * MT - 1) / (16 * MT) * MT * 100 > ((OH + 15) / 16) * 106) MT >>= 1;   // avoid > 6 % more rows
@@ -1011,7 +1056,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     // stages of [A 16 KB | B 16 KB].  Halo mode needs resident weights.
     const long total_smem = (long)kStages * kStageBytes;
     const long w_bytes = ((long)G * L.nsplits * T * L.kchunks * L.b_sub + 1023) / 1024 * 1024;
-    const long a_stage = pack > 1 ? (10 * 18 * 128 + 1023) / 1024 * 1024
+    const long a_stage = halo_s2 ? 4 * (((long)17 * 9 * L.Kc * 2 + 1023) / 1024 * 1024) : pack > 1 ? (10 * 18 * 128 + 1023) / 1024 * 1024
                                   : (halo ? (((long)(16 * MT + 2) * 16 * L.Kc * 2 + 1023) / 1024 * 1024) : kABytesMax);
     static int env_res = -1;
     if (env_res < 0) { const char* e = getenv("DRBA_TC_RESIDENT"); env_res = e ? atoi(e) : 1; }
@@ -1033,7 +1078,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
         }
     }
     L.resident = resident ? 1 : 0;
-    L.halo = halo ? 1 : 0;
+    L.halo = halo ? (halo_s2 ? 2 : 1) : 0;
     L.halo_bo = env_halo_bo;
     L.pack = halo ? pack : 1;
     {
@@ -1069,7 +1114,8 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)S, (cuuint64_t)(W / S), (cuuint64_t)S, (cuuint64_t)(H / S)};
         const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)S * Cin * 2, (cuuint64_t)W * Cin * 2,
                                        (cuuint64_t)S * W * Cin * 2};
-        const cuuint32_t box[5] = {(cuuint32_t)L.Kc, 1, (cuuint32_t)(L.halo ? 16 : L.tile_w), 1, (cuuint32_t)(L.halo ? 16 * L.MT + 2 : L.tile_h * L.MT)};
+        const cuuint32_t box[5] = {(cuuint32_t)L.Kc, 1, (cuuint32_t)(L.halo == 2 ? 9 : (L.halo ? 16 : L.tile_w)), 1,
+                                   (cuuint32_t)(L.halo == 2 ? 17 : (L.halo ? 16 * L.MT + 2 : L.tile_h * L.MT))};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         const CUresult r = encode(&L.ta[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(d.in[i]), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(L.swz_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -35,6 +35,8 @@ def _lrelu(x):
     (32, 64, 33, 50, 1, False),      # packed halo mode (2 pixels per 128-byte line), ragged in both directions
     (16, 16, 37, 52, 1, True),       # packed halo mode (4 pixels per line), residual
     (32, 32, 21, 31, 1, True),       # odd width: falls back to the unpacked halo mode
+    (32, 64, 70, 50, 2, False),      # stride-2 halo mode (four parity-plane boxes per stage), Kc = 32, ragged tiles
+    (64, 32, 34, 18, 2, False),      # stride-2 halo mode, Kc = 64, tile wider than the output
 ])
 def test_conv3x3_tc_vs_torch(cin, cout, h, w, stride, res):
     from drba_b200.ifnet import _tc_conv3x3
