@@ -838,7 +838,10 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                         const int py = g >> 1, px = g & 1;
                         const int OW4 = OW * 4;
                         float* out = reinterpret_cast<float*>(L.out[img]);
-                        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {      // ntile == 64 (checked on the host)
+                        // out_cstride = floats per pixel: 16, or 8 when only the channels 0..7 are wanted (the last IFBlock's
+                        // consumer reads flow and mask only: half the store traffic of the largest lastconv)
+                        const int c_end = cstride == 8 ? (c_hi < 32 ? c_hi : 32) : c_hi;
+                        for (int c0 = c_lo; c0 < c_end; c0 += 32) {      // ntile == 64 (checked on the host)
                             uint32_t rr[32];
                             tc_ld16_nowait(taddr + c0, rr);
                             tc_ld16_nowait(taddr + c0 + 16, rr + 16);
@@ -854,7 +857,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                                 for (int ij = 0; ij < 4; ++ij) {
                                     const int yy = 4 * oy + 2 * py + (ij >> 1), xx = 4 * ox + 2 * px + (ij & 1);
                                     const float4 o = make_float4(v[0 + ij], v[4 + ij], v[8 + ij], v[12 + ij]);
-                                    *reinterpret_cast<float4*>(out + ((size_t)yy * OW4 + xx) * 16 + (c >> 2)) = o;
+                                    *reinterpret_cast<float4*>(out + ((size_t)yy * OW4 + xx) * cstride + (c >> 2)) = o;
                                 }
                             }
                         }
@@ -937,7 +940,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     if (S == 2 && (H % 2 != 0 || W % 2 != 0)) return DRBA_E_ARG;
     if (d.cout_pad <= 0 || d.cout_pad % 16 != 0 || d.cout <= 0 || d.cout > d.cout_pad) return DRBA_E_ARG;
     if (d.epilogue != 0 && d.epilogue != 1) return DRBA_E_ARG;
-    if (d.epilogue == 1 && (d.cout_pad != 64 || d.cout != 52 || G != 4)) return DRBA_E_ARG;
+    if (d.epilogue == 1 && (d.cout_pad != 64 || d.cout != 52 || G != 4 || (d.out_cstride != 16 && d.out_cstride != 8))) return DRBA_E_ARG;
     if (d.out_os != 1 && d.out_os != 2) return DRBA_E_ARG;
     if (d.epilogue == 0 && ((d.out_os == 1 && G != 1) || (d.out_os == 2 && G != 4))) return DRBA_E_ARG;
     if (d.epilogue == 0 && (d.out_cstride < d.cout_pad || d.out_cstride % 8 != 0)) return DRBA_E_ARG;

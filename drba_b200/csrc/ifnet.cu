@@ -225,9 +225,9 @@ static bool env_flag(const char* name)
 
 static int tmp_ok(const float* tmp, int layout, int H, int W, int s)
 {
-    if (!tmp || (layout != 0 && layout != 1) || s <= 0 || H % s != 0 || W % s != 0) return DRBA_E_ARG;
+    if (!tmp || layout < 0 || layout > 2 || s <= 0 || H % s != 0 || W % s != 0) return DRBA_E_ARG;
     if (layout == 0 && ((H / s) % 2 != 0 || (W / s) % 2 != 0)) return DRBA_E_ARG;
-    if (layout == 1 && !aligned16(tmp)) return DRBA_E_ALIGN;
+    if (layout >= 1 && !aligned16(tmp)) return DRBA_E_ALIGN;
     return DRBA_OK;
 }
 
@@ -245,13 +245,14 @@ int drba_ifnet_assemble(const float* img0, const float* img1, const void* f0, co
     if (out_dtype == DRBA_F16 && (out_cstride < (flow ? 64 : 48) || out_cstride % 8 != 0)) return DRBA_E_ARG;
     if (!aligned16(f0) || !aligned16(f1) || !aligned16(out) || (flow && !aligned16(flow))) return DRBA_E_ALIGN;
     if (flow) {
+        if (tmp_layout == 2) return DRBA_E_ARG;       // the 8-channel form carries flow + mask only
         const int rc = tmp_ok(tmp_prev, tmp_layout, H, W, s_prev);
         if (rc != DRBA_OK) return rc;
     }
     AssembleParams p;
     p.img0 = img0; p.img1 = img1; p.f0 = f0; p.f1 = f1;
     p.timestep = timestep; p.timestep_scalar = timestep_scalar; p.flow = flow;
-    p.prev.p = tmp_prev; p.prev.s = flow ? s_prev : 1; p.prev.h13 = flow ? H / s_prev : 1; p.prev.w13 = flow ? W / s_prev : 1;
+    p.prev.p = tmp_prev; p.prev.s = flow ? s_prev : 1; p.prev.h13 = flow ? H / s_prev : 1; p.prev.w13 = flow ? W / s_prev : 1; p.prev.pitch = 16;
     p.out = out; p.out_cstride = out_cstride; p.H = H; p.W = W; p.s = s; p.h = H / s; p.w = W / s;
     const unsigned grid = cdiv((size_t)p.h * p.w, 32);
     cudaStream_t st = as_stream(stream);
@@ -282,7 +283,7 @@ int drba_ifnet_flow_accum(const float* tmp, int tmp_layout, int s, float* flow, 
     const int rc = tmp_ok(tmp, tmp_layout, H, W, s);
     if (rc != DRBA_OK) return rc;
     if (flow && !aligned16(flow)) return DRBA_E_ALIGN;
-    Tmp13 t; t.p = tmp; t.s = s; t.h13 = H / s; t.w13 = W / s;
+    Tmp13 t; t.p = tmp; t.s = s; t.h13 = H / s; t.w13 = W / s; t.pitch = tmp_layout == 2 ? 8 : 16;
     const unsigned grid = cdiv((size_t)H * W, 256);
     if (tmp_layout == 0) ifnet_flow_accum_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(t, flow, planar, accumulate, H, W);
     else ifnet_flow_accum_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(t, flow, planar, accumulate, H, W);
@@ -297,7 +298,7 @@ int drba_ifnet_blend(const float* img0, const float* img1, const float* flow, co
     const int rc = tmp_ok(tmp, tmp_layout, H, W, s);
     if (rc != DRBA_OK) return rc;
     if (flow && !aligned16(flow)) return DRBA_E_ALIGN;
-    Tmp13 t; t.p = tmp; t.s = s; t.h13 = H / s; t.w13 = W / s;
+    Tmp13 t; t.p = tmp; t.s = s; t.h13 = H / s; t.w13 = W / s; t.pitch = tmp_layout == 2 ? 8 : 16;
     const unsigned grid = cdiv((size_t)H * W, kIfThreads);
     if (tmp_layout == 0) ifnet_blend_kernel<0><<<grid, kIfThreads, 0, as_stream(stream)>>>(img0, img1, flow, t, out, H, W);
     else ifnet_blend_kernel<1><<<grid, kIfThreads, 0, as_stream(stream)>>>(img0, img1, flow, t, out, H, W);

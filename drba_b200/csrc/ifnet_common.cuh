@@ -93,6 +93,7 @@ __device__ __forceinline__ void sample_feat16(const FT* __restrict__ f, const Wa
 //               engine's lastconv epilogue
 struct Tmp13 {
     const float* p; int h13, w13, s;   // 13-channel map at 1/s of the full resolution
+    int pitch;                          // TMP_LAYOUT 1: floats per pixel (16; 8 = channels 0..7 only, tmp_layout 2 at the C ABI)
 };
 
 struct Bilin {           // F.interpolate(scale_factor=s, bilinear, align_corners=False) source taps
@@ -125,7 +126,7 @@ __device__ __forceinline__ void load_tmp(const Tmp13& t, int yy, int xx, float* 
 #pragma unroll
         for (int c = 0; c < NC; ++c) v[c] = t.p[(size_t)((C0 + c) * 4 + sub) * h2 * w2 + base];
     } else {
-        const float* q = t.p + ((size_t)yy * t.w13 + xx) * 16;
+        const float* q = t.p + ((size_t)yy * t.w13 + xx) * t.pitch;
         if (C0 % 4 == 0) {
             const float4* q4 = reinterpret_cast<const float4*>(q + C0);
 #pragma unroll

@@ -311,16 +311,18 @@ class IFNetEngine:
             a = [self._buf(("ah", bi, H, W, k), (h2, w2, c // 2), f16) for k in range(nj)]
             p0 = [self._buf(("p0h", bi, H, W, k), (h4, w4, c), f16) for k in range(nj)]
             p1 = [self._buf(("p1h", bi, H, W, k), (h4, w4, c), f16) for k in range(nj)]
-            tmp = [self._buf(("tmp13", bi, H, W, k), (h, w, 16), torch.float32) for k in range(nj)]
+            # the last block's output is read by the blend only (flow + mask): 8 floats per pixel instead of 16
+            tch = 8 if bi == len(_BLOCKS) - 1 else 16
+            tmp = [self._buf(("tmp13", bi, H, W, k), (h, w, tch), torch.float32) for k in range(nj)]
             steps = [(self.tc[f"{name}.conv0a"], h, w, xs, a, h2, w2, c // 2, None),
                      (self.tc[f"{name}.conv0b"], h2, w2, a, p0, h4, w4, c, None)]
             cur, nxt = p0, p1
             for i in range(8):
                 steps.append((self.tc[f"{name}.res{i}"], h4, w4, cur, nxt, h4, w4, c, cur))
                 cur, nxt = nxt, cur
-            steps.append((self.tc[f"{name}.last"], h4, w4, cur, tmp, h4, w4, 16, None))
+            steps.append((self.tc[f"{name}.last"], h4, w4, cur, tmp, h4, w4, tch, None))
             self._conv_program(steps, tag=name)
-            return [(t, 1, s) for t in tmp]
+            return [(t, 2 if tch == 8 else 1, s) for t in tmp]
         # exact engine: NCHW fp32 activations
         outs = []
         for k, j in enumerate(jobs):

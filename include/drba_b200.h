@@ -180,7 +180,8 @@ DRBA_API int drba_conv2d_direct_f32(const float* in, const float* w, const float
  *               out_os 2: ConvTranspose2d(k4,s2,p1) as G = 4 phase convs (g = py*2+px, T = 4):
  *                         [2*OH][2*OW][out_cstride], phase g lands at (2*oy + py, 2*ox + px)  (Head.cnn3)
  *   epilogue 1: lastconv = ConvTranspose2d(Cin,52,4,2,1)+PixelShuffle(2): G = 4 phases (py*2+px),
- *               T = 4, cout_pad = 64, cout = 52; out = NHWC fp32 [4*OH][4*OW][16] (13 used)
+ *               T = 4, cout_pad = 64, cout = 52; out = NHWC fp32 [4*OH][4*OW][out_cstride], out_cstride = 16
+ *               (13 used) or 8 (channels 0..7 only: flow, mask, feat 0..2)
  * ------------------------------------------------------------------------- */
 DRBA_API int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
                               const void* w, const float* bias, int G, int T, const int* dy, const int* dx,
@@ -294,6 +295,8 @@ DRBA_API int drba_axpby_f32(const float* a, float alpha, const float* b, float b
  * flow: [H][W][4] fp32.  "tmp" = a block's lastconv output, 13 channels at 1/s resolution:
  *   tmp_layout 0: ConvTranspose output NCHW fp32 [52][H/2s][W/2s] (exact engine)
  *   tmp_layout 1: pixel-shuffled NHWC fp32 [H/s][W/s][16]       (tensor-core engine)
+ *   tmp_layout 2: the same with 8 floats per pixel (flow + mask + 3 feat channels: what flow_accum / blend read;
+ *                 written by the last IFBlock's lastconv with out_cstride = 8; not accepted by drba_ifnet_assemble)
  *
  * drba_ifnet_assemble: conv input of one IFBlock at 1/s resolution = warp + cat + resize
  *   (IFNet_HDv3.py:151-155 + :85-88).  flow == NULL: first block (39 channels, no warp).

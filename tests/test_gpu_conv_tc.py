@@ -85,6 +85,11 @@ def test_lastconv_tc_vs_torch(cin, h, w):
     err = (got - ref).abs()
     assert (err <= 1e-3 + 1e-3 * ref.abs()).all(), f"max err {err.max().item():.4g}"
     assert (out[:, :, 13:] == 0).all()
+    # 8 floats per pixel: the form the last IFBlock writes for the blend (flow + mask live in channels 0..4)
+    out8 = torch.full((4 * h, 4 * w, 8), float("nan"), dtype=torch.float32, device="cuda")
+    eng._conv_tc(layer, x_nhwc, h, w, out8, h, w, 8)
+    torch.cuda.synchronize()
+    assert torch.equal(out8, out[:, :, :8])
 
 
 def _psnr(a, b):
