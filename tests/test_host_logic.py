@@ -212,3 +212,20 @@ def test_gmfss_host_contract_without_gpu():
             assert tuple(st[net][name].shape) == tuple(shape)
     with pytest.raises(_lib.DrbaError):
         GMFSS(state=st, device="cpu")
+
+
+def test_window_graph_reuse_tree_helpers():
+    """drba_b200/_graphs.py: the nested `reuse` of GMFSS (flows, metrics, tuples of feature maps: models/gmfss.py:71)
+    is flattened depth first and re-created with the same nesting for the static graph inputs."""
+    import torch
+    from drba_b200._graphs import like_tree, tensors_of
+    a, b, c, d = (torch.arange(6, dtype=torch.float32).reshape(2, 3) + k for k in range(4))
+    tree = [a, b, (c, d.t())]           # d.t(): non-contiguous on purpose
+    flat = tensors_of(tree)
+    assert [t.data_ptr() for t in flat] == [a.data_ptr(), b.data_ptr(), c.data_ptr(), d.data_ptr()]
+    twin = like_tree(tree)
+    assert isinstance(twin, list) and isinstance(twin[2], tuple) and len(twin[2]) == 2
+    for x, y in zip(tensors_of(twin), flat):
+        assert x.shape == y.shape and x.dtype == y.dtype and x.is_contiguous() and x.data_ptr() != y.data_ptr()
+        x.copy_(y)
+        assert torch.equal(x, y)
