@@ -9,8 +9,15 @@
 //    <= 128 channels; the accumulator is a [128 lanes x ntile columns] fp32 block of tensor memory;
 //  * per K step ONE tiled TMA load brings the shifted input window into shared memory as K-major,
 //    hardware-swizzled [128 x Kc] A tiles -- zero padding is TMA out-of-bounds fill, so there is no
-//    im2col buffer and no halo logic.  Stride-2 convs view the input as [H/2][2][W/2][2][C] (rank-5
-//    tensor map) so a tap stays a dense box;
+//    im2col buffer.  Stride-2 convs view the input as [H/2][2][W/2][2][C] (rank-5 tensor map) so a
+//    tap stays a dense box;
+//  * HALO MODES (3x3 layers whose weights are resident): the TMA unit moves ~one box line per 3-5
+//    cycles whatever the line length, so instead of one box per tap the tile's whole neighbourhood is
+//    loaded once per K chunk and the nine taps are UMMA descriptor start offsets into it (the swizzle
+//    phase comes from the absolute shared-memory address, so any start offset and any stride between
+//    8-row groups works): stride 1 = one (16 MT + 2) x 16 pixel box for 8-pixel-wide tiles; thin
+//    inputs (16 / 32 channels) PACKED 4 / 2 pixels per 128-byte line; stride 2 = the four parity
+//    planes of the 17 x 9 cell neighbourhood as four boxes of one stage;
 //  * thin layers (Kc = 16 / 32 channels per K step) work on SUPER TILES of 4 / 2 vertically stacked
 //    M tiles so that every TMA box still carries 16 KB (measured: a TMA instruction costs its issuing
 //    thread ~130 cycles regardless of size, which is what bounds layers with 4 KB boxes);
@@ -27,8 +34,14 @@
 //    shared-memory ring that never drains between tiles;
 //  * warp 0 = activation (A) producer, warp 10 = weight (B) producer, warp 1 = tcgen05.mma issuer --
 //    each runs its loop warp-converged with ONE ELECTED lane issuing, which keeps TMA / MMA operands in
-//    uniform registers; warps 2-5 / 6-9 = two epilogue groups that alternate tiles over a
-//    double-buffered TMEM accumulator (the epilogue of tile i overlaps the main loop of tile i+1);
+//    uniform registers; warps 2-5 / 6-9 = two epilogue groups that drain EVERY tile together (one M
+//    tile of the super tile each, or half of the columns) from a double-buffered TMEM accumulator
+//    (the epilogue of tile i overlaps the main loop of tile i+1).  The plain epilogue exists in two
+//    template variants: one lane per pixel row, or rows moved four lanes per pixel through a
+//    swizzled per-warp staging tile (coalesced residual / result traffic for wide rows);
+//  * a tcgen05.mma with M = 128 costs >= ~115 cycles for any N <= 64 (the A operand arrives one
+//    32-byte row segment per cycle), so at IFNet's channel counts the MMA count, not the FLOP count,
+//    sets the main-loop time;
 //  * consecutive layers (a whole IFBlock: conv0a, conv0b, 8 x ResConv, lastconv) are chained inside
 //    the launch with a grid-wide barrier (release/acquire counter in global memory) instead of a
 //    kernel boundary; up to two independent images (the two interpolated frames of a DRBA window)
@@ -76,7 +89,6 @@ struct alignas(64) LayerDev {
     int halo;               // 1: 3x3 stride-1 layer whose taps are descriptor offsets into ONE halo tile per K chunk
     int nst;                // ring stages used by this layer
     int a_base, a_stride;   // byte offset of the activation ring and bytes per stage
-    int halo_bo;            // experiment: write the descriptor's base_offset field
     int pack;               // packed halo mode: pixels per 128-byte line (2 or 4), else 1
     int staged;             // epilogue moves residual / result through the per-warp staging tile
     int ntile, nsplits, cout_pad, cout;
@@ -975,20 +987,17 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     for (int cand = d.cout_pad < kMaxNTile ? d.cout_pad : kMaxNTile; cand >= 16; cand -= 16)
         if (d.cout_pad % cand == 0) { ntile = cand; break; }
     if (!ntile) return DRBA_E_UNSUPPORTED;
-    const int b_bytes_pre = kMaxNTile * L.Kc * 2;
-    (void)b_bytes_pre;
     // halo mode: a 3x3 stride-1 layer loads ONE (16*MT+2) x 16 pixel neighbourhood per K chunk and runs the nine
     // taps as descriptor offsets into it (8-pixel-wide tiles keep every 8-row core group contiguous; the 16-pixel
     // pitch keeps the swizzle phase identical for all groups) -- 4x fewer activation bytes than one box per tap.
     // Needs the weights resident (checked below once ntile is final).
-    static int env_halo = -1, env_halo_bo = -1, env_pack = -1, env_s2 = 1;
+    static int env_halo = -1, env_pack = -1, env_s2 = 1;
     if (env_halo < 0) {
         const char* e = getenv("DRBA_TC_HALO"); env_halo = e ? atoi(e) : 1;
-        e = getenv("DRBA_TC_HALO_BO"); env_halo_bo = e ? atoi(e) : 0;
         e = getenv("DRBA_TC_PACK"); env_pack = e ? atoi(e) : 1;
         e = getenv("DRBA_TC_HALO_S2"); env_s2 = e ? atoi(e) : 1;
     }
-    bool halo = env_halo && (S == 1 || (S == 2 && env_halo >= 1 && env_s2)) && T == 9 && G == 1 && d.epilogue == 0 && !d.bgemm;
+    bool halo = env_halo && (S == 1 || (S == 2 && env_s2)) && T == 9 && G == 1 && d.epilogue == 0 && !d.bgemm;
     if (halo)
         for (int t = 0; t < 9; ++t)
             if (d.dy[t] != t / 3 - 1 || d.dx[t] != t % 3 - 1) halo = false;
@@ -1066,8 +1075,6 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     bool resident = env_res && !d.bgemm && w_bytes + 2 * a_stage <= total_smem && w_bytes <= (long)kBRegion + 32768;
     if (halo && !resident) {
         // fall back to one box per tap: redo the tile choice without the halo constraint
-        drba_conv_layer d2 = d;
-        (void)d2;
         halo = false;
         static thread_local int depth = 0;
         if (depth == 0) {
@@ -1082,7 +1089,6 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     }
     L.resident = resident ? 1 : 0;
     L.halo = halo ? (halo_s2 ? 2 : 1) : 0;
-    L.halo_bo = env_halo_bo;
     L.pack = halo ? pack : 1;
     {
         static int env_staged = -1;

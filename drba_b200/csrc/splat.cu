@@ -235,6 +235,36 @@ constexpr int kGatherMinChannels = 9;
 
 using namespace drba;
 
+namespace drba {
+// four consecutive pixels per thread (H * W % 4 == 0): same arithmetic as invert_flow_resolve_kernel, 16-byte stores
+__global__ void __launch_bounds__(kSplatThreads)
+invert_flow_resolve4_kernel(float* __restrict__ acc, float* __restrict__ out, int N, int H, int W)
+{
+    const size_t HW = (size_t)H * W, Q = HW >> 2;
+    const size_t i = (size_t)blockIdx.x * kSplatThreads + threadIdx.x;
+    if (i >= (size_t)N * Q) return;
+    const int n = (int)(i / Q);
+    const size_t r = (i - (size_t)n * Q) << 2;
+    float4* a4 = reinterpret_cast<float4*>(acc) + (size_t)n * HW + r;
+    const float big = (float)(H > W ? H : W);           // rife.py:69-70
+    float ox[4], oy[4];
+    float4 a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = a4[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float den = a[k].z + 0.0000001f;
+        const float mask = a[k].z / den;                // splat_avg(ones) (rife.py:63-64)
+        float x = -1.0f * (a[k].x / den), y = -1.0f * (a[k].y / den);
+        if (mask < 0.999f) { x = big; y = big; }
+        ox[k] = x * 2.0f; oy[k] = y * 2.0f;             // rife.py:72-73
+    }
+    *reinterpret_cast<float4*>(out + ((size_t)n * 2) * HW + r) = make_float4(ox[0], ox[1], ox[2], ox[3]);
+    *reinterpret_cast<float4*>(out + ((size_t)n * 2 + 1) * HW + r) = make_float4(oy[0], oy[1], oy[2], oy[3]);
+}
+}  // namespace drba
+
 extern "C" {
 
 size_t drba_softsplat_workspace_bytes(int N, int C, int H, int W, int mode)
@@ -331,7 +361,10 @@ int drba_rife_invert_flow_f32(const float* flow_t0, float* out, int N, int H, in
     const unsigned grid = cdiv((size_t)N * H * W, kSplatThreads);
     invert_flow_scatter_kernel<<<grid, kSplatThreads, 0, st>>>(flow_t0, (float*)ws, N, H, W);
     DRBA_RETURN_IF_LAUNCH_FAILED();
-    invert_flow_resolve_kernel<<<grid, kSplatThreads, 0, st>>>((float*)ws, out, N, H, W);
+    if (((size_t)H * W) % 4 == 0 && aligned16(out))
+        invert_flow_resolve4_kernel<<<cdiv((size_t)N * H * W / 4, kSplatThreads), kSplatThreads, 0, st>>>((float*)ws, out, N, H, W);
+    else
+        invert_flow_resolve_kernel<<<grid, kSplatThreads, 0, st>>>((float*)ws, out, N, H, W);
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
 }
