@@ -240,7 +240,7 @@ def run_reference(args, rank):
                              "sample": f"{k} window(s) ({nout} output frames) of the same 1088x1920 clip; oracle port "
                                        f"(torch fp32 CPU convs + C splat/warp); /root/reference cannot travel to the GPU box"},
             "e2e": {"value": round(fps, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -481,10 +481,32 @@ def main():
             line["softsplat_roofline"] = splat
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """The result line goes to the process's ORIGINAL stdout; see _quiet_stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """stdout carries exactly one JSON line (the driver parses it).  Libraries write there too (NCCL prints its
+    version banner to fd 1 when NCCL_DEBUG is set on the box), so fd 1 is pointed at stderr for the run and the
+    result is written to a private duplicate of the original fd."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
 if __name__ == "__main__":
+    _quiet_stdout()
     main()
