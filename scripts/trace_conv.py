@@ -1,5 +1,15 @@
 #!/usr/bin/env python
-"""Decode the clock64 pipeline trace of CTA 0 for one conv layer / program (debug aid)."""
+"""Decode the clock64 pipeline trace of CTA 0 for one conv layer / program (debug aid).
+
+The trace points are compiled out of the product library (they cost the producer / MMA warps 10-15 % on issue-bound
+layers).  Build a tracing variant and point the loader at it:
+
+    cd drba_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo \
+        -Xcompiler -fPIC,-fvisibility=hidden -DDRBA_TC_TRACE=1 -c conv_tc.cu -o build/conv_tc_T.o && \
+    nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../ab/libT.so \
+        $(ls build/*.o | grep -v conv_tc) build/conv_tc_T.o -lcuda
+    DRBA_B200_LIB=$PWD/../../ab/libT.so python scripts/trace_conv.py block4.res.x2 block4.conv0a
+"""
 import os
 import sys
 
