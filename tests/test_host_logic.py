@@ -229,3 +229,26 @@ def test_window_graph_reuse_tree_helpers():
         assert x.shape == y.shape and x.dtype == y.dtype and x.is_contiguous() and x.data_ptr() != y.data_ptr()
         x.copy_(y)
         assert torch.equal(x, y)
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Every ctypes signature in drba_b200/_lib.py has as many arguments as the C prototype in
+    include/drba_b200.h, pointers where the header has pointers and scalars where it has scalars."""
+    import ctypes
+    import re
+    from drba_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "drba_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", " ", hdr)
+    protos = dict(re.findall(r"\b(drba_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, params in protos.items():
+        params = " ".join(params.split())
+        args = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        _, argtypes = _lib.SIGNATURES[name]
+        assert len(args) == len(argtypes), (name, len(args), len(argtypes))
+        for decl, ct in zip(args, argtypes):
+            is_ptr_c = "*" in decl
+            is_ptr_py = ct in (ctypes.c_void_p, ctypes.c_char_p) or isinstance(ct, type(ctypes.POINTER(ctypes.c_int))) \
+                or (isinstance(ct, type) and issubclass(ct, ctypes.Array))
+            assert is_ptr_c == is_ptr_py, (name, decl, ct)
