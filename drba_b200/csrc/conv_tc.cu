@@ -39,9 +39,9 @@
 //    (the epilogue of tile i overlaps the main loop of tile i+1).  The plain epilogue exists in two
 //    template variants: one lane per pixel row, or rows moved four lanes per pixel through a
 //    swizzled per-warp staging tile (coalesced residual / result traffic for wide rows);
-//  * a tcgen05.mma with M = 128 costs >= ~115 cycles for any N <= 64 (the A operand arrives one
+//  * a tcgen05.mma with M = 128 costs ~115-121 cycles for N = 32 / 64 (an operand arrives at about one
 //    32-byte row segment per cycle), so at IFNet's channel counts the MMA count, not the FLOP count,
-//    sets the main-loop time;
+//    sets the main-loop time: the ceiling of this GEMM view is N/256 of the tensor peak;
 //  * consecutive layers (a whole IFBlock: conv0a, conv0b, 8 x ResConv, lastconv) are chained inside
 //    the launch with a grid-wide barrier (release/acquire counter in global memory) instead of a
 //    kernel boundary; up to two independent images (the two interpolated frames of a DRBA window)
