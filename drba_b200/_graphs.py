@@ -53,6 +53,7 @@ class WindowGraphs:
                     dst.copy_(src)
         graph.replay()
         _lib.count(n_kernels)                 # kernels inside the replayed graph (recorded at capture)
+        _lib.check_async("window graph")
         output = [frames[pt] if pt >= 0 else o.clone() for o, pt in zip(outs, passthrough)]
         return output, new_reuse
 

@@ -68,6 +68,8 @@ SIGNATURES = {
     "drba_conv_tc_f16": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     "drba_conv_tc_program_f16": (_I, [_P, _I, _I, _P, _P]),
     "drba_conv_tc_debug_trace": (_I, [_P]),
+    "drba_conv_tc_status": (_I, []),
+    "drba_check_scene_f32": (_I, [_P, _P, _c.c_longlong, _c.c_longlong, _I, _I, _I, _F, _P, _P, _P]),
     "drba_ifnet_assemble": (_I, [_P, _P, _P, _P, _I, _P, _F, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
     "drba_ifnet_flow_accum": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P]),
     "drba_ifnet_blend": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P]),
@@ -184,6 +186,14 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def check_async(what):
+    """Sticky device-side errors of work already enqueued (the grid-barrier time-out of a persistent conv program,
+    include/drba_b200.h: drba_conv_tc_status); a plain host read, no synchronisation."""
+    rc = lib().drba_conv_tc_status()
+    if rc != 0:
+        check(rc, what)
 
 
 def check(rc, what):

@@ -34,6 +34,7 @@ class Workspace:
     every drba_* op leaves it zero on exit (include/drba_b200.h)."""
 
     _pool = {}
+    _retired = []      # outgrown buffers stay alive: CUDA graphs captured earlier have their addresses baked in
 
     @classmethod
     def get(cls, nbytes, device):
@@ -41,6 +42,8 @@ class Workspace:
                torch.cuda.current_stream(device).cuda_stream)
         buf = cls._pool.get(key)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                cls._retired.append(buf)
             buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
             _lib.check(_lib.lib().drba_workspace_clear(buf.data_ptr(), buf.numel(), stream_ptr(device)),
                        "drba_workspace_clear")

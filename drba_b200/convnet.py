@@ -33,7 +33,10 @@ _sync_words = {}
 
 
 def _sync(device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """Grid-barrier words of the persistent programs: one pair per (device, stream) -- programs on one stream run
+    one after the other and may share them, programs on different streams must not."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
     t = _sync_words.get(key)
     if t is None:
         t = torch.zeros(2, dtype=torch.int32, device=device)

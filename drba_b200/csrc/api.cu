@@ -13,6 +13,7 @@ const char* drba_error_string(int code)
         case DRBA_E_WORKSPACE: return "workspace missing or too small";
         case DRBA_E_UNSUPPORTED: return "unsupported configuration";
         case DRBA_E_ALIGN: return "pointer is not 16-byte aligned";
+        case DRBA_E_BARRIER: return "a persistent conv program timed out at its grid barrier (CTAs not co-resident): results are invalid";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -60,6 +60,7 @@ __device__ __forceinline__ Footprint footprint(int x, int y, float fx, float fy)
 __device__ __forceinline__ float splat_den(float d, int eps_mode) {
     if (eps_mode == DRBA_EPS_ADD) return d + 0.0000001f;
     if (eps_mode == DRBA_EPS_ZERO) return d == 0.0f ? 1.0f : d;
+    if (eps_mode == DRBA_EPS_NONE) return d;
     return d < 0.0000001f ? 0.0000001f : d;
 }
 

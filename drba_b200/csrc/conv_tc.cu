@@ -106,6 +106,7 @@ struct alignas(64) LayerDev {
 struct Program {
     int nlayers, nimg;
     unsigned* sync;         // [2] grid-barrier arrival counter, exit counter (zero between launches)
+    unsigned* err;          // sticky error word in mapped pinned host memory (bit 0: grid barrier timed out)
     int dbg;
     int pad_;
     long long* trace;       // debug: clock64 stamps of CTA 0 (NULL in production)
@@ -280,13 +281,20 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // grid-wide barrier between two layers of a program: every CTA arrives once per layer
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
+// A CTA that never arrives (the grid was not co-resident: MPS / MIG / a foreign kernel holding SMs) would hang the
+// GPU, so the wait is bounded -- but a time-out is an ERROR, not a fall-through: it sets the sticky word in mapped
+// host memory that drba_conv_tc_program_f16 / drba_conv_tc_status return as DRBA_E_BARRIER from then on.
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target, unsigned* err) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     unsigned v;
     unsigned spins = 0;
     do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while (v < target && ++spins < (1u << 24));   // bail out instead of hanging the GPU if a CTA is missing
+    } while (v < target && ++spins < (1u << 24));
+    if (v < target && err) {
+        atomicOr_system(err, 1u);
+        __threadfence_system();
+    }
 }
 
 
@@ -893,7 +901,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             // this CTA's MMAs are done: the next layer's resident weights may overwrite the weight region while
             // the grid barrier is pending (weights do not depend on other CTAs)
             if (warp == 10) load_resident_weights(li + 1);
-            if (threadIdx.x == 0) { TC_TRACE(li * 256 + 202); grid_barrier(prog.sync, (unsigned)(li + 1) * gridDim.x); TC_TRACE(li * 256 + 203); }
+            if (threadIdx.x == 0) { TC_TRACE(li * 256 + 202); grid_barrier(prog.sync, (unsigned)(li + 1) * gridDim.x, prog.err); TC_TRACE(li * 256 + 203); }
             stage_tables(li + 1);
             __syncthreads();
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -1146,6 +1154,36 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
 
 static long long* g_trace = nullptr;
 
+// sticky error word of the persistent programs: mapped pinned host memory, written by the kernel with system scope
+// and read by the host WITHOUT synchronising (one-time allocation at the first multi-layer launch)
+static unsigned* g_err_host = nullptr;
+static unsigned* g_err_dev = nullptr;
+
+static int ensure_err_word()
+{
+    if (g_err_host) return DRBA_OK;
+    void* h = nullptr;
+    cudaError_t e = cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) return (int)e;
+    memset(h, 0, 64);
+    void* d = nullptr;
+    e = cudaHostGetDevicePointer(&d, h, 0);
+    if (e != cudaSuccess) { cudaFreeHost(h); return (int)e; }
+    g_err_host = (unsigned*)h; g_err_dev = (unsigned*)d;
+    return DRBA_OK;
+}
+
+// CTAs of conv_tc_kernel that can be resident at once on the current device (the grid barrier needs all of them)
+template <typename K>
+static int resident_ctas(K kernel, size_t smem)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTcThreads, smem) != cudaSuccess) return 0;
+    return sms * per_sm;
+}
+
 }  // namespace drba
 
 using namespace drba;
@@ -1171,8 +1209,14 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
         e = getenv("DRBA_TC_DBG"); env_dbg = e ? atoi(e) : 0;
         e = getenv("DRBA_TC_GRID"); env_grid = e ? atoi(e) : 0;
     }
+    if (nlayers > 1) {
+        const int rc = ensure_err_word();
+        if (rc != DRBA_OK) return rc;
+        if (*(volatile unsigned*)g_err_host) return DRBA_E_BARRIER;      // an earlier program lost a CTA: results are invalid
+    }
     Program prog;
     prog.nlayers = nlayers; prog.nimg = nimg; prog.sync = (unsigned*)sync_ws; prog.dbg = env_dbg; prog.pad_ = 0;
+    prog.err = g_err_dev;
     prog.trace = g_trace;
     int max_tiles = 0;
     for (int i = 0; i < nlayers; ++i) {
@@ -1180,17 +1224,21 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
         if (rc != DRBA_OK) return rc;
         if (prog.L[i].total_tiles > max_tiles) max_tiles = prog.L[i].total_tiles;
     }
-    int grid = max_tiles < kNumSMs ? max_tiles : kNumSMs;
-    if (env_grid > 0 && env_grid < grid) grid = env_grid;
     static bool attr_set = false;
+    static int max_resident = 0;
     const size_t smem = (size_t)kBRegion + (size_t)kStages * kABytesMax + 1024 + 8 * kStagingBytes;   // ring + alignment + epilogue staging
     if (!attr_set) {
         cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // the grid barrier needs every CTA resident: never launch more than the device can hold at once
+        max_resident = resident_ctas(conv_tc_kernel<true, true>, smem);
         attr_set = true;
     }
+    if (max_resident < 1) return DRBA_E_UNSUPPORTED;
+    int grid = max_tiles < max_resident ? max_tiles : max_resident;
+    if (env_grid > 0 && env_grid < grid) grid = env_grid;
     bool full = false;
     for (int i = 0; i < nlayers; ++i) {
         const drba_conv_layer& d = layers[i];
@@ -1217,6 +1265,14 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
                                 : (staged ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, prog) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, prog));
     if (le != cudaSuccess) return (int)le;
     DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+int drba_conv_tc_status(void)
+{
+    // no synchronisation: reports what the device has written so far (call after a stream / device sync for a
+    // definite answer about the work enqueued before it)
+    if (g_err_host && *(volatile unsigned*)g_err_host) return DRBA_E_BARRIER;
     return DRBA_OK;
 }
 

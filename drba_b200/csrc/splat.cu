@@ -285,7 +285,7 @@ int drba_softsplat_f32_variant(const float* in, const float* flow, const float* 
 {
     if (N < 0 || C < 0 || H < 0 || W < 0) return DRBA_E_ARG;
     if (mode < DRBA_SPLAT_SUM || mode > DRBA_SPLAT_SOFT) return DRBA_E_ARG;
-    if (eps_mode < DRBA_EPS_ADD || eps_mode > DRBA_EPS_CLIP) return DRBA_E_ARG;
+    if (eps_mode < DRBA_EPS_ADD || eps_mode > DRBA_EPS_NONE) return DRBA_E_ARG;
     if (variant < 0 || variant > 3) return DRBA_E_ARG;
     if ((size_t)N * C * H * W == 0) return DRBA_OK;
     if (!in || !flow || !out) return DRBA_E_ARG;

@@ -109,14 +109,26 @@ def num_iterations(n_frames):
 
 
 def shard_ranges(n_iterations, world):
-    """Contiguous, balanced ranges [a, b) of loop iterations, one per rank."""
+    """Contiguous, balanced ranges [a, b) of loop iterations, one per rank.  Ranks without work (world >
+    n_iterations) get (None, None): interpolate_shard emits nothing for them, so head and tail are emitted exactly
+    once (by the shard that starts at 0 and the last non-empty one; rank 0 when the clip has no iteration at all)."""
     base, rem = divmod(n_iterations, world)
     out, a = [], 0
     for r in range(world):
         b = a + base + (1 if r < rem else 0)
-        out.append((a, b))
+        out.append((a, b) if (b > a or (n_iterations == 0 and r == 0)) else (None, None))
         a = b
     return out
+
+
+def shard_reuse(model, Ia, Ib):
+    """The `reuse` the sequential loop hands to iteration a, rebuilt from frames a, a+1.
+    RIFE (models/rife.py:109): (flow21, flow12, f2, f1) of the previous window = calc_flow(Ia, Ib) pair-swapped;
+    GMFSS / GMFSS_UNION (models/gmfss.py:71, gmfss_union.py:98): Model.reuse(Ia, Ib) pair-swapped."""
+    if hasattr(model, "shard_reuse"):
+        return model.shard_reuse(Ia, Ib)
+    f01, f10, fa, fb = model.calc_flow(Ia, Ib)
+    return (f10, f01, fb, fa)
 
 
 def interpolate_shard(model, frames, src_fps, dst_fps, times=-1, check_scene=None, a=0, b=None):
@@ -130,6 +142,11 @@ def interpolate_shard(model, frames, src_fps, dst_fps, times=-1, check_scene=Non
     b = n_it if b is None else b
     calc_t = make_calc_t(src_fps, dst_fps, times)
     scene = check_scene if check_scene is not None else _no_scene
+    if a is None:
+        return          # a rank without work (shard_ranges: world > n_iterations)
+    a, b = max(0, min(a, n_it)), max(0, min(b, n_it))
+    if a == b and n_it > 0:
+        return          # an empty range of a non-empty clip emits nothing (head / tail belong to non-empty shards)
     first, last = a == 0, b == n_it
 
     if first:
@@ -142,8 +159,7 @@ def interpolate_shard(model, frames, src_fps, dst_fps, times=-1, check_scene=Non
         left_scene = bool(scene(frames[a], frames[a + 1]))
         prev_left = bool(scene(frames[a - 1], frames[a]))
         if not prev_left and not left_scene:
-            f01, f10, fa, fb = model.calc_flow(frames[a], frames[a + 1])
-            reuse = (f10, f01, fb, fa)
+            reuse = shard_reuse(model, frames[a], frames[a + 1])
         else:
             reuse = None
     for j in range(a, b):

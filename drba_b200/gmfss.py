@@ -11,8 +11,7 @@ from `flownet.pkl` (state["flownet"]).  A different `flow_estimator(img_a, img_b
 injected (the component parity tests inject the reference GMFlow's flows from tests/golden); with neither,
 `Model.reuse` raises DrbaError -- there is no silent fallback.
 
-Differences a caller can observe: frames are returned as fp32 (the reference returns the autocast dtype);
-the entries of `reuse` holding features are tuples of NHWC fp16 tensors (opaque to infer.py).
+Differences a caller can observe: the entries of `reuse` holding features are tuples of NHWC fp16 tensors (opaque to infer.py).
 """
 import os
 
@@ -162,7 +161,8 @@ class Model:
 
 
 class GMFSS:
-    def __init__(self, weights=r'weights/train_log_gmfss', scale=1.0, device=None, state=None, flow_estimator=None, graphs=None):
+    def __init__(self, weights=r'weights/train_log_gmfss', scale=1.0, device=None, state=None, flow_estimator=None, graphs=None,
+                 output_dtype=torch.float16):
         if device is None:
             device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         device = torch.device(device)
@@ -173,6 +173,9 @@ class GMFSS:
                 raise FileNotFoundError(os.path.join(weights, 'fusionnet.pkl'))
             state = load_gmfss_state(weights)
         self.model = Model(state, device, flow_estimator)
+        # the reference returns frames in the autocast dtype (fp16 on CUDA); torch.float32 keeps GridNet's
+        # unpacked fp32 output as it is
+        self.output_dtype = output_dtype
         self.scale = scale
         self.pad_size = 64
         # graphs: every distinct window shape is captured into a CUDA graph once and replayed (_graphs.py).  Default: on
@@ -192,8 +195,15 @@ class GMFSS:
             elif t == 1:
                 output.append(I1)
             else:
-                output.append(self.model.inference(I0, I1, reuse, timestep0=t, timestep1=1 - t))
+                output.append(self.model.inference(I0, I1, reuse, timestep0=t, timestep1=1 - t).to(self.output_dtype))
         return output
+
+    @torch.inference_mode()
+    def shard_reuse(self, Ia, Ib):
+        """`reuse` as the sequential loop leaves it after the window that ends on (Ia, Ib): Model.reuse(Ia, Ib) with
+        its pairs swapped (last line of inference_ts_drba) -- lets a frame-window shard start mid-stream (driver.py)."""
+        r = self.model.reuse(Ia, Ib, self.scale)
+        return [value for pair in zip(r[1::2], r[0::2]) for value in pair]
 
     @torch.inference_mode()
     def inference_ts_drba(self, I0, I1, I2, ts, reuse=None, linear=False):
@@ -218,11 +228,11 @@ class GMFSS:
             elif 0 < t < 1:
                 t = 1 - t
                 drm = calc_drm_gmfss(t, flow10, flow12, metric10, metric12, linear)
-                output.append(self.model.inference(I1, I0, reuseI1I0, timestep0=drm['drm1t_t01'], timestep1=drm['drm0t_t01']))
+                output.append(self.model.inference(I1, I0, reuseI1I0, timestep0=drm['drm1t_t01'], timestep1=drm['drm0t_t01']).to(self.output_dtype))
             elif 1 < t < 2:
                 t = t - 1
                 drm = calc_drm_gmfss(t, flow10, flow12, metric10, metric12, linear)
-                output.append(self.model.inference(I1, I2, reuseI1I2, timestep0=drm['drm1t_t12'], timestep1=drm['drm2t_t12']))
+                output.append(self.model.inference(I1, I2, reuseI1I2, timestep0=drm['drm1t_t12'], timestep1=drm['drm2t_t12']).to(self.output_dtype))
         # next reuseI1I0 = reverse(current reuseI1I2)
         reuse = [value for pair in zip(reuseI1I2[1::2], reuseI1I2[0::2]) for value in pair]
         return output, reuse

@@ -41,7 +41,7 @@ def load_union_rife_state(weights_dir):
 
 class GMFSS_UNION:
     def __init__(self, weights='weights/train_log_gmfss_union', scale=1.0, device=None, state=None, rife_state=None,
-                 flow_estimator=None, precision="fp16", graphs=None):
+                 flow_estimator=None, precision="fp16", graphs=None, output_dtype=torch.float16):
         if device is None:
             device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         device = torch.device(device)
@@ -53,6 +53,7 @@ class GMFSS_UNION:
             state = load_gmfss_state(weights)
             rife_state = load_union_rife_state(weights)
         self.model = UnionModel(state, device, flow_estimator)
+        self.output_dtype = output_dtype      # the reference returns the autocast dtype (fp16 on CUDA)
         self.ifnet = IFNetEngine(rife_state, device, precision)
         self.scale = scale
         self.scale_list = [16 / self.scale, 8 / self.scale, 4 / self.scale, 2 / self.scale, 1 / self.scale]
@@ -77,8 +78,15 @@ class GMFSS_UNION:
                 I0s = resize_bilinear(I0, scale_factor=0.5)
                 I1s = resize_bilinear(I1, scale_factor=0.5)
                 rife = self.ifnet.forward(I0s, I1s, float(t), self.scale_list)
-                output.append(self.model.inference(I0, I1, reuse, timestep0=t, timestep1=1 - t, rife=rife))
+                output.append(self.model.inference(I0, I1, reuse, timestep0=t, timestep1=1 - t, rife=rife).to(self.output_dtype))
         return output
+
+    @torch.inference_mode()
+    def shard_reuse(self, Ia, Ib):
+        """`reuse` as the sequential loop leaves it after the window that ends on (Ia, Ib): Model.reuse(Ia, Ib) with
+        its pairs swapped (last line of inference_ts_drba) -- lets a frame-window shard start mid-stream (driver.py)."""
+        r = self.model.reuse(Ia, Ib, self.scale)
+        return [value for pair in zip(r[1::2], r[0::2]) for value in pair]
 
     @torch.inference_mode()
     def inference_ts_drba(self, I0, I1, I2, ts, reuse=None, linear=False):
@@ -108,7 +116,7 @@ class GMFSS_UNION:
                 tmap = resize(drm_rife['drm_t1_t01'], I0s.shape[2:])
                 rife = self.ifnet.forward(I1s, I0s, tmap, self.scale_list)
                 output.append(self.model.inference(I1, I0, reuseI1I0, timestep0=drm_gmfss['drm1t_t01'],
-                                                   timestep1=drm_gmfss['drm0t_t01'], rife=rife))
+                                                   timestep1=drm_gmfss['drm0t_t01'], rife=rife).to(self.output_dtype))
             elif 1 < t < 2:
                 t = t - 1
                 drm_gmfss = calc_drm_gmfss(t, flow10, flow12, metric10, metric12, linear)
@@ -116,7 +124,7 @@ class GMFSS_UNION:
                 tmap = resize(drm_rife['drm_t1_t12'], I0s.shape[2:])
                 rife = self.ifnet.forward(I1s, I2s, tmap, self.scale_list)
                 output.append(self.model.inference(I1, I2, reuseI1I2, timestep0=drm_gmfss['drm1t_t12'],
-                                                   timestep1=drm_gmfss['drm2t_t12'], rife=rife))
+                                                   timestep1=drm_gmfss['drm2t_t12'], rife=rife).to(self.output_dtype))
         # next reuseI1I0 = reverse(current reuseI1I2)
         reuse = [value for pair in zip(reuseI1I2[1::2], reuseI1I2[0::2]) for value in pair]
         return output, reuse

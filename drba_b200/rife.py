@@ -5,12 +5,13 @@ methods (``inference_ts``, ``calc_flow``, ``inference_ts_drba``) with the refere
 meaning and return structure; the work runs in libdrba_b200.so through ``IFNetEngine``.
 
 Differences a caller can observe (DESIGN.md "boundary"):
-* the per-frame feature maps handed around in ``reuse`` / returned by ``calc_flow`` are the
-  engine's [H, W, 16] channels-last tensors (the reference returns [1, 16, H, W]); they are
-  opaque to infer.py, which only passes them back in;
-* ``precision='fp32'`` (default here) computes everything in fp32; ``precision='fp16'`` runs the
-  convolutions on the tensor cores with fp16 operands like the reference under torch.autocast
-  (rife.py:26, :78); flows, DRM maps, warps and splats are fp32 in both;
+* the per-frame feature maps handed around in ``reuse`` / returned by ``calc_flow`` have the
+  reference's shape [1, 16, H, W] but are channels-last VIEWS of the engine's [H, W, 16] buffers
+  (fp16 with the default engine, like the reference's features under autocast); feature maps
+  passed back in may have either layout (a contiguous NCHW tensor is repacked);
+* ``precision='fp16'`` (default: what the reference does on CUDA under torch.autocast, rife.py:26,
+  :78) runs the convolutions on the tensor cores with fp16 operands; ``precision='fp32'`` is the
+  exact engine (CUDA cores, fp32 everywhere); flows, DRM maps, warps and splats are fp32 in both;
 * only the DRM map the caller consumes is computed (rife.py:99 / :105 use one of the two);
 * ``graphs=True`` (default): each distinct window shape (frame size, timestamp list, with/without
   ``reuse``) is captured once into a CUDA graph and replayed, which removes the ~150 kernel-launch
@@ -30,9 +31,22 @@ from .ops import rife_invert_flow
 from .weights import load_ifnet_state
 
 
+def _nhwc(f):
+    """Feature map in the engine's layout [H, W, 16]: a [1, 16, H, W] tensor (reference layout) is viewed -- or, if
+    it is not channels-last in memory, repacked -- as [H, W, 16]."""
+    if f.dim() == 4:
+        f = f[0].permute(1, 2, 0)
+    return f if f.is_contiguous() else f.contiguous()
+
+
+def _nchw_view(f):
+    """[H, W, 16] engine buffer -> the reference's [1, 16, H, W] shape (a view, no copy)."""
+    return f.permute(2, 0, 1).unsqueeze(0) if f.dim() == 3 else f
+
+
 class RIFE:
     def __init__(self, weights='weights/train_log_rife_426_heavy', scale=1.0,
-                 device=None, precision="fp32", state=None, graphs=True):
+                 device=None, precision="fp16", state=None, graphs=True):
         if device is None:
             device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         device = torch.device(device)
@@ -70,12 +84,12 @@ class RIFE:
         """models/rife.py:41-75: block0-only bidirectional flow at 1/16 scale, inverted by
         forward-warping it onto itself, holes <- max(H, W)."""
         a3, b3 = a[:, :3], b[:, :3]
-        f0 = self.ifnet.encode(a3) if f0 is None else f0
-        f1 = self.ifnet.encode(b3) if f1 is None else f1
+        f0 = self.ifnet.encode(a3) if f0 is None else _nhwc(f0)
+        f1 = self.ifnet.encode(b3) if f1 is None else _nhwc(f1)
         flow = self.ifnet.block0_flow(a3, b3, f0, f1, 0.5, self.scale_list[0])
         flow01 = rife_invert_flow(flow[:, :2])
         flow10 = rife_invert_flow(flow[:, 2:])
-        return flow01, flow10, f0, f1
+        return flow01, flow10, _nchw_view(f0), _nchw_view(f1)
 
     @torch.inference_mode()
     def inference_ts_drba(self, I0, I1, I2, ts, reuse=None, linear=False):
@@ -99,11 +113,22 @@ class RIFE:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src.float())
         if reuse:
-            for dst, src in zip(s_reuse, reuse):
-                if dst.data_ptr() != src.data_ptr():
-                    dst.copy_(src)
+            # `reuse` may alias this graph's own static inputs (the f1 of the previous window of the same shape IS
+            # s_reuse[2], and belongs in s_reuse[3] now): copies that read a static buffer go first, from a
+            # snapshot when more than one of them could chain
+            static = {d.data_ptr() for d in s_reuse}
+            pending = [(d, s) for d, s in zip(s_reuse, reuse) if d.data_ptr() != s.data_ptr()]
+            first = [(d, s) for d, s in pending if s.data_ptr() in static]
+            if len(first) > 1:
+                first = [(d, s.clone()) for d, s in first]
+            for d, s in first:
+                d.copy_(s)
+            for d, s in pending:
+                if s.data_ptr() not in static:
+                    d.copy_(s)
         graph.replay()
         _lib.count(n_kernels)      # kernels inside the replayed graph (recorded at capture)
+        _lib.check_async("RIFE window graph")
         output = []
         for o, pt in zip(outs, passthrough):
             output.append(frames[pt] if pt >= 0 else o.clone())   # t in {0,1,2}: the input tensor itself (rife.py:89-94)
@@ -159,13 +184,13 @@ class RIFE:
             elif 0 < t < 1:
                 t = 1 - t
                 drm = calc_drm_rife(t, flow10, flow12, linear, only='drm_t1_t01')
-                reqs.append((I1, I0, drm['drm_t1_t01'], f1, f0))
+                reqs.append((I1, I0, drm['drm_t1_t01'], _nhwc(f1), _nhwc(f0)))
                 slots.append(len(output))
                 output.append(None)
             elif 1 < t < 2:
                 t = t - 1
                 drm = calc_drm_rife(t, flow10, flow12, linear, only='drm_t1_t12')
-                reqs.append((I1, I2, drm['drm_t1_t12'], f1, f2))
+                reqs.append((I1, I2, drm['drm_t1_t12'], _nhwc(f1), _nhwc(f2)))
                 slots.append(len(output))
                 output.append(None)
         if reqs:

@@ -19,7 +19,7 @@ from . import _lib
 from ._torch_util import Workspace, f32c, ptr, require_cuda, stream_ptr
 
 MODES = {"sum": 0, "avg": 1, "linear": 2, "soft": 3}
-EPS = {None: 0, "addeps": 0, "zeroeps": 1, "clipeps": 2}
+EPS = {None: 0, "addeps": 0, "zeroeps": 1, "clipeps": 2, "?": 3}
 
 
 def softsplat(tenIn, tenFlow, tenMetric, strMode: str, _variant=0):
@@ -32,8 +32,8 @@ def softsplat(tenIn, tenFlow, tenMetric, strMode: str, _variant=0):
     if parts[0] == "soft":
         assert tenMetric is not None
     sub = parts[1] if len(parts) > 1 else None
-    if sub not in EPS:      # the reference silently skips normalisation tweaks it does not know
-        sub = None
+    if sub not in EPS:      # an unknown suffix matches no branch of softsplat.py:273-290: raw denominator
+        sub = "?"
     mode, eps = MODES[parts[0]], EPS[sub]
     if parts[0] in ("sum", "avg"):
         tenMetric = None

@@ -1,12 +1,9 @@
 """Host-side helpers around the hot path -- mirror of models/utils/tools.py (sizing, frame
-conversion) and models/pytorch_msssim (scene detection).  Frame resizes run through
-drba_resize_bilinear_f32; scene detection is 32x32 work (out of the hot path) and
-stays a few torch ops."""
-import math
+conversion, scene detection).  Frame resizes run through drba_resize_bilinear_f32, scene detection
+(check_scene + models/pytorch_msssim ssim_matlab) through drba_check_scene_f32 (one kernel, no host sync)."""
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from .ops import resize_bilinear
 
@@ -47,42 +44,75 @@ def to_out(tenInp, src_size):
     return to_cv2(resize(tenInp, src_size))
 
 
-def _gauss1d(n, sigma=1.5):
-    g = torch.tensor([math.exp(-(x - n // 2) ** 2 / float(2 * sigma ** 2)) for x in range(n)])
-    return g / g.sum()
+def check_scene_async(x1, x2, scdet_threshold=0.3, out=None):
+    """tools.py:27-30 as ONE kernel (csrc/scene.cu: 32x32 bilinear thumbnails + ssim_matlab + compare), nothing
+    synchronises.  x1, x2: [1,3,H,W] fp32 CUDA frames.  Returns (ssim, flag): device tensors of one element each
+    (flag 1 = scene cut), or writes into `out = (ssim_tensor, flag_tensor)` (may be mapped pinned host memory)."""
+    from . import _lib
+    from ._torch_util import ptr, require_cuda, stream_ptr
+    require_cuda(x1, x2)
+    a, b = x1.float().contiguous(), x2.float().contiguous()
+    if a.dim() != 4 or a.shape[0] != 1 or a.shape[1] != 3 or a.shape != b.shape:
+        raise ValueError("check_scene expects two [1,3,H,W] frames of the same size")
+    H, W = int(a.shape[2]), int(a.shape[3])
+    if out is None:
+        out = (torch.empty(1, dtype=torch.float32, device=a.device), torch.empty(1, dtype=torch.int32, device=a.device))
+    with torch.cuda.device(a.device):
+        with _lib.launch("check_scene", 1, nbytes=float(2 * 3 * 32 * 32 * 16)):
+            rc = _lib.lib().drba_check_scene_f32(ptr(a), ptr(b), 0, 0, 1, H, W, float(scdet_threshold), ptr(out[0]), ptr(out[1]),
+                                                 stream_ptr(a.device))
+    _lib.check(rc, "drba_check_scene_f32")
+    return out
 
 
 def ssim_matlab(img1, img2, window_size=11):
-    """models/pytorch_msssim/__init__.py:83-136: SSIM with a 3-D Gaussian window over (C, H, W),
-    replicate padding; written with the separable form of the same window."""
-    mx, mn = float(img1.max()), float(img1.min())
-    L = (255 if mx > 128 else 1) - (-1 if mn < -0.5 else 0)
-    g = _gauss1d(min(window_size, img1.shape[2], img1.shape[3])).to(img1.device, img1.dtype)
-    n = g.numel()
-    pad = 5
-
-    def blur(x):
-        x = F.pad(x.unsqueeze(1), (pad,) * 6, mode='replicate')
-        x = F.conv3d(x, g.view(1, 1, n, 1, 1))
-        x = F.conv3d(x, g.view(1, 1, 1, n, 1))
-        return F.conv3d(x, g.view(1, 1, 1, 1, n))
-
-    mu1, mu2 = blur(img1), blur(img2)
-    mu1_sq, mu2_sq, mu1_mu2 = mu1 * mu1, mu2 * mu2, mu1 * mu2
-    sigma1_sq = blur(img1 * img1) - mu1_sq
-    sigma2_sq = blur(img2 * img2) - mu2_sq
-    sigma12 = blur(img1 * img2) - mu1_mu2
-    C1, C2 = (0.01 * L) ** 2, (0.03 * L) ** 2
-    v1 = 2.0 * sigma12 + C2
-    v2 = sigma1_sq + sigma2_sq + C2
-    return (((2 * mu1_mu2 + C1) * v1) / ((mu1_sq + mu2_sq + C1) * v2)).mean()
+    """models/pytorch_msssim/__init__.py:83-136 on two [1,3,32,32]-or-larger CUDA frames: the SSIM value as a
+    one-element device tensor (the kernel works on 32x32 thumbnails, which is the only way the reference calls it)."""
+    if tuple(img1.shape[2:]) != (32, 32) or window_size != 11:
+        raise ValueError("drba_b200.tools.ssim_matlab serves check_scene's call: 32x32 frames, window 11")
+    return check_scene_async(img1, img2, 0.0)[0]
 
 
 def check_scene(x1, x2, scdet_threshold=0.3):
-    """tools.py:27-30."""
-    x1 = F.interpolate(x1.float(), (32, 32), mode='bilinear', align_corners=False)
-    x2 = F.interpolate(x2.float(), (32, 32), mode='bilinear', align_corners=False)
-    return bool(ssim_matlab(x1, x2) < scdet_threshold)
+    """tools.py:27-30, same signature and result (a Python bool: this form waits for the kernel; the driver loops
+    use SceneDetector, which does not)."""
+    return bool(check_scene_async(x1, x2, scdet_threshold)[1].item())
+
+
+class SceneDetector:
+    """Scene flags without stalling the stream.  submit(a, b) enqueues the check of a frame pair on
+    the current stream and returns a ticket; result(ticket) returns the bool.  The kernel writes its flag into pinned
+    host memory that the device sees directly, so result() only waits on the ticket's event -- which has long
+    completed when the driver loop asks one window later (the reference stalls three times per pair)."""
+
+    def __init__(self, device, threshold=0.3, depth=64):
+        self.device = torch.device(device)
+        self.threshold = float(threshold)
+        self.depth = depth
+        self._ssim = torch.zeros(depth, dtype=torch.float32).pin_memory()
+        self._flag = torch.zeros(depth, dtype=torch.int32).pin_memory()
+        self._events = [None] * depth
+        self._n = 0
+
+    def submit(self, a, b):
+        k = self._n % self.depth
+        self._n += 1
+        check_scene_async(a, b, self.threshold, out=(self._ssim[k:k + 1], self._flag[k:k + 1]))
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._events[k] = ev
+        return k
+
+    def result(self, ticket):
+        self._events[ticket].synchronize()
+        return bool(self._flag[ticket].item())
+
+    def ssim(self, ticket):
+        self._events[ticket].synchronize()
+        return float(self._ssim[ticket].item())
+
+    def __call__(self, a, b):
+        return self.result(self.submit(a, b))
 
 
 # ---- fused frame ingest / egress (SURVEY.md 8f-1) ----------------------------------------------------

@@ -41,10 +41,12 @@ extern "C" {
 #define DRBA_E_WORKSPACE (-2)   /* workspace missing or too small                  */
 #define DRBA_E_UNSUPPORTED (-3) /* valid request this build cannot serve           */
 #define DRBA_E_ALIGN (-4)       /* pointer not aligned as required (16 B)          */
+#define DRBA_E_BARRIER (-5)     /* a persistent conv program timed out at its grid barrier: results invalid (sticky) */
 
 /* softsplat modes / eps variants: models/softsplat/softsplat.py:260-267, :273-290 */
 enum { DRBA_SPLAT_SUM = 0, DRBA_SPLAT_AVG = 1, DRBA_SPLAT_LINEAR = 2, DRBA_SPLAT_SOFT = 3 };
-enum { DRBA_EPS_ADD = 0, DRBA_EPS_ZERO = 1, DRBA_EPS_CLIP = 2 };
+enum { DRBA_EPS_ADD = 0, DRBA_EPS_ZERO = 1, DRBA_EPS_CLIP = 2,
+       DRBA_EPS_NONE = 3 /* unknown "-suffix": the reference divides by the raw denominator (:273-290 fall through) */ };
 /* padding of the backward warp: warplayer.py:22 (border) / MetricNet.py:20 (zeros) */
 enum { DRBA_PAD_BORDER = 0, DRBA_PAD_ZEROS = 1 };
 /* activation dtypes of the conv engine */
@@ -154,6 +156,19 @@ DRBA_API int drba_frame_ingest_u8(const unsigned char* in_hwc, float* out_chw, i
 DRBA_API int drba_frame_egress_u8(const float* in_chw, unsigned char* out_hwc, int H, int W, int OH, int OW, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Scene-cut detection (csrc/scene.cu): check_scene(x1, x2, threshold) of models/utils/tools.py:27-30 =
+ * bilinear 32x32 thumbnails (align_corners=False) + ssim_matlab (models/pytorch_msssim/__init__.py:83-136:
+ * 11^3 Gaussian volume window, replicate padding, value range probed from x1) + `ssim < threshold`, one CTA per
+ * frame pair, no host synchronisation (the reference has three per pair).
+ * Pair i reads the NCHW [3][H][W] fp32 frames x1 + i * pair_stride1 and x2 + i * pair_stride2 (strides in
+ * elements; npairs = 1 for two separate frames; a contiguous clip [N][3][H][W] checks all N - 1 neighbour pairs
+ * with x2 = x1 + 3HW and both strides 3HW).  ssim_out [npairs] / flag_out [npairs] (1 = scene cut) may be NULL
+ * (not both) and may point to mapped pinned host memory.
+ * ------------------------------------------------------------------------- */
+DRBA_API int drba_check_scene_f32(const float* x1, const float* x2, long long pair_stride1, long long pair_stride2,
+                                  int npairs, int H, int W, float threshold, float* ssim_out, int* flag_out, void* stream);
+
+/* ---------------------------------------------------------------------------
  * fp32 direct convolution (exact engine).  Generic form covering every conv on the
  * IFNet path (models/rife_426_heavy/IFNet_HDv3.py:11-25 conv, :28-47 Head, :50-59 ResConv,
  * :80 lastconv ConvTranspose2d(4,2,1) as four phase launches):
@@ -223,6 +238,12 @@ typedef struct drba_conv_layer {
     int bgemm;
 } drba_conv_layer;
 DRBA_API int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nimg, void* sync_ws, void* stream);
+/* The grid barrier of a program needs every CTA resident: the launcher clamps the grid to what the device can hold
+ * (cudaOccupancyMaxActiveBlocksPerMultiprocessor x SM count).  If CTAs still fail to arrive in time (MPS / MIG / a
+ * foreign kernel holding SMs) the wait is abandoned so that the GPU does not hang, and a STICKY error word in mapped
+ * host memory is set: drba_conv_tc_program_f16 returns DRBA_E_BARRIER from then on, and drba_conv_tc_status() (no
+ * synchronisation; a plain host read) reports it for work that was replayed from a CUDA graph. */
+DRBA_API int drba_conv_tc_status(void);
 /* debug: while a device buffer of 4096 int64 is registered, CTA 0 of every conv launch writes clock64() stamps
  * of its pipeline events into it (NULL switches tracing off; scripts/trace_conv.py decodes). */
 DRBA_API int drba_conv_tc_debug_trace(void* dev_buf_4096_i64);

@@ -10,6 +10,7 @@ _SO = os.path.join(_HERE, "libdrba_oracle.so")
 
 MODES = {"sum": 0, "avg": 1, "linear": 2, "soft": 3}
 EPS = {None: 0, "addeps": 0, "zeroeps": 1, "clipeps": 2}
+EPS_UNKNOWN = 3   # any other suffix: no branch of softsplat.py:273-290 fires, raw denominator
 
 
 def build(force=False):
@@ -60,7 +61,7 @@ def _p(a):
 def softsplat(ten_in, flow, metric, mode):
     """numpy NCHW float32 restatement of softsplat(tenIn, tenFlow, tenMetric, strMode)."""
     parts = mode.split("-")
-    m, e = MODES[parts[0]], EPS[parts[1] if len(parts) > 1 else None]
+    m, e = MODES[parts[0]], EPS.get(parts[1] if len(parts) > 1 else None, EPS_UNKNOWN)
     x, f, mt = _f32(ten_in), _f32(flow), _f32(metric)
     if m == 0:
         assert mt is None

@@ -26,7 +26,7 @@
 
 /* mode / eps enums shared with include/drba_b200.h (same numeric values) */
 enum { ORC_SUM = 0, ORC_AVG = 1, ORC_LINEAR = 2, ORC_SOFT = 3 };
-enum { ORC_ADDEPS = 0, ORC_ZEROEPS = 1, ORC_CLIPEPS = 2 };
+enum { ORC_ADDEPS = 0, ORC_ZEROEPS = 1, ORC_CLIPEPS = 2, ORC_NOEPS = 3 /* unknown suffix: no branch of :273-290 fires */ };
 
 /* ------------------------------------------------------------------------ */
 /* Summation splat.                                                          */
@@ -128,7 +128,7 @@ ORC_API int orc_softsplat(const float* in, const float* flow, const float* metri
                 float d = den[p];
                 if (eps_mode == ORC_ADDEPS) d = d + 0.0000001f;          /* :277,:280 */
                 else if (eps_mode == ORC_ZEROEPS) d = (d == 0.0f) ? 1.0f : d; /* :283 */
-                else d = d < 0.0000001f ? 0.0000001f : d;               /* :286 */
+                else if (eps_mode == ORC_CLIPEPS) d = d < 0.0000001f ? 0.0000001f : d; /* :286 */
                 dst[p] = num[p] / d;
             }
         }

@@ -351,3 +351,16 @@ def test_ifnet_assemble_coalesced_kernel_matches_per_pixel_kernel(monkeypatch, s
     # neighbouring fp16 number (eps = 9.8e-4)
     np.testing.assert_allclose(b, a, rtol=2e-3, atol=1e-3)
     assert (a == b).mean() > 0.9
+
+
+@pytest.mark.parametrize("variant", [0, 3])
+def test_softsplat_unknown_suffix_no_eps(variant):
+    """An unknown '-suffix' divides by the raw denominator (softsplat.py:273-290 fall through): NaN holes."""
+    import os
+    from drba_b200.softsplat import softsplat
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "splat_noeps_golden.npz"))
+    for mode, key, metric in (("soft-foo", "soft_foo", d["metric"]), ("linear-bar", "linear_bar", np.abs(d["metric"]))):
+        got = softsplat(cu(d["x"]), cu(d["flow"]), cu(metric), mode, _variant=variant).cpu().numpy()
+        want = d[key]
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(want), rtol=1e-4, atol=1e-4 * float(np.nanmax(np.abs(want))))

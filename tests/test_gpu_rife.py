@@ -24,7 +24,8 @@ def _run(g, tag, state):
         flips = (got == big) != (want == big)
         assert flips.mean() < 1e-3
         np.testing.assert_allclose(got[~flips], want[~flips], rtol=0, atol=2e-3)
-    feat = f1.permute(2, 0, 1)[None].cpu().numpy()
+    assert tuple(f1.shape) == (1, 16) + tuple(I1.shape[2:])      # the reference's layout (models/rife.py:75)
+    feat = f1.cpu().numpy()
     np.testing.assert_allclose(feat, g[f"{tag}_f1"], rtol=0, atol=1e-4)
     y = m.inference_ts(I0, I1, [0.4])[0]
     np.testing.assert_allclose(y.cpu().numpy(), g[f"{tag}_ts0.4"], rtol=0, atol=TOL)

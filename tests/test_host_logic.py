@@ -118,6 +118,64 @@ def test_shards_reproduce_the_sequential_run(world, with_cuts):
         assert len(seq) == int(round((len(frames) - 1) * 2.5)) + 2 or len(seq) > 50
 
 
+@pytest.mark.parametrize("n_frames,world", [(4, 4), (3, 4), (2, 4), (2, 1), (5, 8)])
+def test_more_ranks_than_iterations(n_frames, world):
+    """world > n_iterations: surplus ranks emit nothing; head and tail appear exactly once."""
+    from drba_b200 import driver
+    frames = _clip(n_frames)
+    m = FakeModel()
+    seq = list(driver.interpolate_sequence(m, frames, 24.0, 60.0))
+    parts = []
+    for a, b in driver.shard_ranges(driver.num_iterations(n_frames), world):
+        parts += list(driver.interpolate_shard(m, frames, 24.0, 60.0, a=a, b=b))
+    assert len(parts) == len(seq)
+    for x, y in zip(parts, seq):
+        assert torch.equal(x, y)
+
+
+class FakeGmfss:
+    """Stand-in with the GMFSS interface (no calc_flow; `reuse` is a 6-list with swapped pairs)."""
+    scale, pad_size = 1.0, 64
+
+    def _reuse(self, a, b):
+        return [a - b, b - a + 0.5, a * 2, b * 2, a * 3 + 1, b * 3 + 1]
+
+    def shard_reuse(self, Ia, Ib):
+        r = self._reuse(Ia, Ib)
+        return [v for pair in zip(r[1::2], r[0::2]) for v in pair]
+
+    def inference_ts(self, I0, I1, ts):
+        return [I0 if t == 0 else (I1 if t == 1 else I0 * (1 - t) + I1 * t) for t in ts]
+
+    def inference_ts_drba(self, I0, I1, I2, ts, reuse=None, linear=False):
+        r10 = self._reuse(I1, I0) if reuse is None else reuse
+        r12 = self._reuse(I1, I2)
+        out = []
+        for t in ts:
+            if t == 1:
+                out.append(I1)
+            elif t < 1:
+                out.append(I1 * t + I0 * (1 - t) + 0.01 * r10[0] + 0.001 * r10[5])
+            else:
+                out.append(I1 * (2 - t) + I2 * (t - 1) + 0.01 * r12[0] + 0.001 * r12[5])
+        return out, [v for pair in zip(r12[1::2], r12[0::2]) for v in pair]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gmfss_style_model_shards(world):
+    """Models without calc_flow (GMFSS / GMFSS_UNION) rebuild `reuse` through shard_reuse()."""
+    from drba_b200 import driver
+    frames = _clip(11)
+    m = FakeGmfss()
+    seq = list(driver.interpolate_sequence(m, frames, 24.0, 60.0))
+    parts = []
+    for a, b in driver.shard_ranges(driver.num_iterations(len(frames)), world):
+        parts += list(driver.interpolate_shard(m, frames, 24.0, 60.0, a=a, b=b))
+    assert len(parts) == len(seq)
+    for x, y in zip(parts, seq):
+        assert torch.equal(x, y)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
