@@ -62,7 +62,8 @@ constexpr int kBRegion = 98304;        // resident mode: all weight tiles of the
 constexpr int kMaxNTile = 128;
 constexpr int kMaxTapsTc = 9;
 constexpr int kMaxGroups = 4;
-constexpr int kTmemCols = 256;         // two accumulators of <= 128 columns
+constexpr int kAccBufs = 4;            // accumulator ring in tensor memory
+constexpr int kTmemCols = kAccBufs * kMaxNTile;   // four accumulators of <= 128 columns = all 512 columns (one CTA per SM)
 constexpr int kMaxLayers = DRBA_CONV_MAX_LAYERS;
 constexpr int kMaxImages = 2;
 
@@ -91,6 +92,7 @@ struct alignas(64) LayerDev {
     int a_base, a_stride;   // byte offset of the activation ring and bytes per stage
     int pack;               // packed halo mode: pixels per 128-byte line (2 or 4), else 1
     int staged;             // epilogue moves residual / result through the per-warp staging tile
+    int alt;                // epilogue groups take alternate tiles (whole accumulator each) instead of splitting every tile
     int ntile, nsplits, cout_pad, cout;
     int swz_bytes;          // 32 / 64 / 128
     int b_sub;              // bytes of one weight tile (padded to the swizzle period)
@@ -317,7 +319,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], acc_empty[2], b_full;
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_full[kAccBufs], acc_empty[kAccBufs], b_full;
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[512];
     __shared__ __align__(16) float s_slope[512];
@@ -368,7 +370,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
         asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[0].ta[0]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[0].tb) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+        for (int b = 0; b < kAccBufs; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
         mbar_init(&b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -510,7 +512,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             if (resident) bres_phase ^= 1u;
             int tl = 0;
             for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount, ++tl) {
-                const uint32_t buf = tcount & 1u, use = tcount >> 1;
+                const uint32_t buf = tcount & (uint32_t)(kAccBufs - 1), use = tcount / (uint32_t)kAccBufs;
                 int r = idx / mtiles;
                 const int nsplit = r % nsplits; r /= nsplits;
                 const int g = r % G;
@@ -585,12 +587,19 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             // Both groups work on EVERY tile (half of the accumulator each), so a tile's drain latency is halved and
             // layers with one or two tiles per SM do not leave a group idle: M tiles split when the super tile
             // stacks several, columns split otherwise.
-            const int mt_lo = MT >= 2 ? (int)group * (MT >> 1) : 0, mt_hi = MT >= 2 ? mt_lo + (MT >> 1) : 1;
+            // ALTERNATE mode (layers with many tiles per CTA): group g drains the WHOLE accumulator of the tiles with
+            // tcount % 2 == g, so the drains of consecutive tiles overlap each other (a drain is a latency chain:
+            // TMEM load -> residual -> activation -> staging -> store) and, with four accumulators, the MMA warp runs
+            // up to three tiles ahead; measured tile period of block4.res before: 3700 cycles, of which MMA issue 1900.
+            const bool alt = L.alt != 0;
+            const int mt_lo = alt ? 0 : (MT >= 2 ? (int)group * (MT >> 1) : 0), mt_hi = alt ? MT : (MT >= 2 ? mt_lo + (MT >> 1) : 1);
             const int chalf = ((ntile >> 1) + 15) & ~15;
-            const int c_lo = MT >= 2 ? 0 : (group ? chalf : 0), c_hi = MT >= 2 ? ntile : (group ? ntile : chalf);
+            const int c_lo = (alt || MT >= 2) ? 0 : (group ? chalf : 0), c_hi = (alt || MT >= 2) ? ntile : (group ? ntile : chalf);
             int tl = 0;
             for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount, ++tl) {
-                const uint32_t buf = tcount & 1u, use = tcount >> 1;
+                const uint32_t buf = tcount & (uint32_t)(kAccBufs - 1), use = tcount / (uint32_t)kAccBufs;
+                // alternate mode: this tile belongs to the other group (which signs off for both, see below)
+                if (alt && (tcount & 1u) != group) continue;
                 const int m = idx % mtiles;
                 int r = idx / mtiles;
                 const int nsplit = r % nsplits; r /= nsplits;
@@ -888,7 +897,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 // accumulator drained: hand the buffer back to the MMA warp
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                if (lane == 0) { mbar_arrive(&acc_empty[buf]); if (alt) mbar_arrive(&acc_empty[buf]); }   // 8 arrivals free a buffer
             }
         }
 
@@ -1239,6 +1248,13 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
     if (max_resident < 1) return DRBA_E_UNSUPPORTED;
     int grid = max_tiles < max_resident ? max_tiles : max_resident;
     if (env_grid > 0 && env_grid < grid) grid = env_grid;
+    {
+        // alternate-tile epilogue where a CTA walks at least four tiles of the layer (DRBA_TC_ALT: 0 never, 1 auto, 2 always)
+        static int env_alt = -1;
+        if (env_alt < 0) { const char* e = getenv("DRBA_TC_ALT"); env_alt = e ? atoi(e) : 1; }
+        for (int i = 0; i < nlayers; ++i)
+            prog.L[i].alt = env_alt == 2 || (env_alt == 1 && prog.L[i].total_tiles >= 4 * grid) ? 1 : 0;
+    }
     bool full = false;
     for (int i = 0; i < nlayers; ++i) {
         const drba_conv_layer& d = layers[i];

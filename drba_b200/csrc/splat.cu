@@ -226,7 +226,7 @@ invert_flow_resolve_kernel(float* __restrict__ acc, float* __restrict__ out, int
 // csrc/splat_gather.cu
 size_t splat_gather_workspace_bytes(int N, int H, int W);
 int splat_gather_launch(const float* in, const float* flow, const float* metric, float* out,
-                        int N, int C, int H, int W, int mode, int eps_mode, void* ws, cudaStream_t st);
+                        int N, int C, int H, int W, int mode, int eps_mode, void* ws, cudaStream_t st, bool tile);
 // the list-building cost of the gather path is independent of C: it wins once the scatter path would
 // need three or more 4-channel accumulator groups
 constexpr int kGatherMinChannels = 9;
@@ -286,7 +286,7 @@ int drba_softsplat_f32_variant(const float* in, const float* flow, const float* 
     if (N < 0 || C < 0 || H < 0 || W < 0) return DRBA_E_ARG;
     if (mode < DRBA_SPLAT_SUM || mode > DRBA_SPLAT_SOFT) return DRBA_E_ARG;
     if (eps_mode < DRBA_EPS_ADD || eps_mode > DRBA_EPS_NONE) return DRBA_E_ARG;
-    if (variant < 0 || variant > 3) return DRBA_E_ARG;
+    if (variant < 0 || variant > 4) return DRBA_E_ARG;
     if ((size_t)N * C * H * W == 0) return DRBA_OK;
     if (!in || !flow || !out) return DRBA_E_ARG;
     if ((mode == DRBA_SPLAT_LINEAR || mode == DRBA_SPLAT_SOFT) && !metric) return DRBA_E_ARG;
@@ -295,18 +295,19 @@ int drba_softsplat_f32_variant(const float* in, const float* flow, const float* 
     if (!aligned16(ws)) return DRBA_E_ALIGN;
     const int has_w = mode != DRBA_SPLAT_SUM ? 1 : 0;
     // variant: 0 = automatic, 1 = scalar atomics (the reference kernel's scheme), 2 = vector-red scatter,
-    //          3 = owner-computes gather (csrc/splat_gather.cu)
-    if (variant == 3 || (variant == 0 && C + has_w >= kGatherMinChannels)) {
+    //          3 = owner-computes gather, per-target loads (csrc/splat_gather.cu), 4 = the same with TMA-staged
+    //          source tiles (what variant 0 picks for C + weight >= 9)
+    if (variant == 3 || variant == 4 || (variant == 0 && C + has_w >= kGatherMinChannels)) {
         const size_t need = splat_gather_workspace_bytes(N, H, W);
         if (ws_bytes >= need) {
-            const int rc = splat_gather_launch(in, flow, metric, out, N, C, H, W, mode, eps_mode, ws, as_stream(stream));
+            const int rc = splat_gather_launch(in, flow, metric, out, N, C, H, W, mode, eps_mode, ws, as_stream(stream), variant != 3);
             if (rc != DRBA_E_UNSUPPORTED) return rc;
-        } else if (variant == 3) {
+        } else if (variant == 3 || variant == 4) {
             return DRBA_E_WORKSPACE;
         }
     }
     if (variant == 2) variant = 0;
-    if (variant == 3) variant = 0;
+    if (variant == 3 || variant == 4) variant = 0;
     const size_t groups_fit = ws_bytes / group_bytes;
     const int cc_max = (int)(groups_fit * 4 > (size_t)(C + has_w) ? (size_t)C : groups_fit * 4 - has_w);
     cudaStream_t st = as_stream(stream);

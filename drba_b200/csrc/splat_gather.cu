@@ -23,6 +23,7 @@
 // HBM traffic: in read once + out written once + ~100 B/pixel of list traffic (C-independent).
 // The workspace keeps the library-wide contract (all-zero on entry, all-zero on exit): counters
 // return to zero in step 3, {offset, count} pairs and lists are cleared by a bulk memset after step 4.
+#include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -37,7 +38,8 @@ struct GatherWs {
     int* count;        // [total]            zero on entry / exit
     int2* offcnt;      // [total]            {offset, count}
     int2* entries;     // [4 * total]   {key, corner weight}
-    int* block_sums;   // [nblocks_scan + 1]
+    int* block_sums;   // [nblocks_scan + 4]
+    int* done;         // [N * tiles of 64 x 16 targets]: 1 = served by the TMA-staged tile kernel
 };
 
 __device__ __forceinline__ void corner_targets(const Footprint& f, int H, int W, bool& nw, bool& ne, bool& sw, bool& se)
@@ -249,11 +251,19 @@ template <int MODE, int CCH>
 __global__ void __launch_bounds__(kGThreads)
 splat_gather_kernel(const float* __restrict__ in, const float* __restrict__ metric,
                     float* __restrict__ out, int2* __restrict__ offcnt, int2* __restrict__ entries,
-                    int N, int C, int H, int W, int eps_mode, int dbg)
+                    int N, int C, int H, int W, int eps_mode, int dbg, const int* __restrict__ done, int tiles_x, int tiles_y)
 {
     const size_t HW = (size_t)H * W;
     const size_t p = (size_t)blockIdx.x * kGThreads + threadIdx.x;
-    const bool live = p < (size_t)N * HW;
+    bool live = p < (size_t)N * HW;
+    if (done && live) {
+        // tiles already served by splat_gather_tile_kernel (64 x 16 targets, see below) -- except their targets with
+        // more than 8 entries, which that kernel leaves to this one
+        const int im = (int)(p / HW);
+        const size_t r = p - (size_t)im * HW;
+        const int y = (int)(r / W), x = (int)(r - (size_t)y * W);
+        if (done[(im * tiles_y + (y >> 4)) * tiles_x + (x >> 6)] && offcnt[p].y <= 8) live = false;
+    }
     const size_t pc = live ? p : 0;
     const int img = (int)(pc / HW);
     const size_t rp = pc - (size_t)img * HW;
@@ -330,6 +340,243 @@ splat_gather_kernel(const float* __restrict__ in, const float* __restrict__ metr
     }
 }
 
+
+// ---- step 4, tile flavour: sources staged in shared memory by TMA -------------------------------------------------
+// The per-target gather above reads every source value through the L1 data stage: 4 entries x C channels scalar
+// loads per target, two 128-byte wavefronts each because the sources of 32 adjacent targets are displaced by the
+// flow -- ncu shows the L1 wavefront rate, not HBM, as its bound.  Here a CTA owns a 64 x 16 tile of
+// targets.  The entries of a smooth flow all point into a compact source rectangle (tile + displacement spread), so:
+//   * the CTA reduces the bounding box of its entries' sources; if it fits kBoxW x kBoxH,
+//   * ONE TMA box load per 4-channel chunk ([4][kBoxH][kBoxW] fp32 out of the NCHW tensor viewed as a rank-3
+//     [N*C][H][W] map, zero fill outside the image) lands in a 3-stage ring, the elected thread runs two chunks ahead,
+//   * every thread (four targets) reads its <= 8 sorted entries' values from shared memory (adjacent lanes, adjacent
+//     words: conflict-free), accumulates in the reference order and writes each output plane row-coalesced.
+// Each source value crosses L2 -> SM once per tile instead of once per (entry, target); the arithmetic and its order
+// are those of gather_regs, so results stay bit-identical to the CPU restatement for sum / avg / linear.
+// Tiles whose sources do not fit the box (folds, large divergence) and targets with more than 8 entries take the
+// per-target path above -- same results, old speed.
+constexpr int kTileW = 64, kTileH = 16, kTileThreads = 256;     // four targets per thread: rows r, r + 4, r + 8, r + 12
+constexpr int kTPT = kTileW * kTileH / kTileThreads;
+// three box sizes (a tensor map each): a tile takes the smallest one its sources fit, so the L2 -> SM traffic follows
+// the flow's actual spread (72 x 20: 1.4x the tile, 96 x 32: 3x); the ring holds as many stages as fit 96 KB
+constexpr int kBoxC = 4, kNumBoxes = 3, kMaxBoxStages = 4;
+constexpr int kRingBytes = 98304;
+struct BoxMaps { CUtensorMap m[kNumBoxes]; };
+__constant__ int c_box_w[kNumBoxes] = {72, 80, 96};
+__constant__ int c_box_h[kNumBoxes] = {20, 24, 32};
+static const int h_box_w[kNumBoxes] = {72, 80, 96}, h_box_h[kNumBoxes] = {20, 24, 32};
+
+__device__ __forceinline__ uint32_t sg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sg_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sg_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sg_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sg_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = sg_smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void sg_tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(sg_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTileThreads, 2)
+splat_gather_tile_kernel(const __grid_constant__ BoxMaps maps, const float* __restrict__ in, const float* __restrict__ metric,
+                         float* __restrict__ out, int2* __restrict__ offcnt, int2* __restrict__ entries, int* __restrict__ done,
+                         int N, int C, int H, int W, int eps_mode, int tiles_x, int tiles_y)
+{
+    extern __shared__ __align__(128) float sg_box[];             // [stages][kBoxC][box h][box w]
+    __shared__ uint64_t full_bar[kMaxBoxStages];
+    __shared__ int s_min[2], s_max[2];
+    constexpr int NE = 8;
+    constexpr bool FAST = MODE == DRBA_SPLAT_SOFT;
+    const int tid = threadIdx.x;
+    const size_t HW = (size_t)H * W;
+    int tile = blockIdx.x;
+    const int img = tile / (tiles_x * tiles_y);
+    tile -= img * tiles_x * tiles_y;
+    const int ty0 = (tile / tiles_x) * kTileH, tx0 = (tile % tiles_x) * kTileW;
+    const int x = tx0 + (tid & 63);
+    const float* met = metric ? metric + (size_t)img * HW : nullptr;
+    const float* inb = in + (size_t)img * C * HW;
+
+    if (tid == 0) {
+        for (int s = 0; s < kMaxBoxStages; ++s) sg_mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_min[0] = s_min[1] = 0x7fffffff; s_max[0] = s_max[1] = -0x7fffffff;
+    }
+    __syncthreads();
+
+    // ---- my two targets: lists into registers, sorted into the reference's summation order -------------------------
+    int n[kTPT]; bool live[kTPT]; unsigned rp[kTPT];
+    unsigned src[kTPT][NE]; float wc[kTPT][NE], wg[kTPT][NE], den[kTPT], rden[kTPT];
+    int2* ent[kTPT];
+    int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -0x7fffffff, mxy = -0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < kTPT; ++j) {
+        const int y = ty0 + (tid >> 6) + (kTileH / kTPT) * j;
+        live[j] = x < W && y < H;
+        rp[j] = live[j] ? (unsigned)y * (unsigned)W + (unsigned)x : 0u;
+        int2 oc = make_int2(0, 0);
+        if (live[j]) oc = offcnt[(size_t)img * HW + rp[j]];
+        n[j] = oc.y;
+        ent[j] = entries + (size_t)oc.x;
+        int key[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            key[e] = 0x7fffffff; wc[j][e] = 0.0f;
+            if (e < n[j] && n[j] <= NE) { const int2 v = ent[j][e]; key[e] = v.x; wc[j][e] = __int_as_float(v.y); }
+        }
+#pragma unroll
+        for (int r = 0; r < NE; ++r)
+#pragma unroll
+            for (int i = (r & 1); i + 1 < NE; i += 2) cswap(key[i], wc[j][i], key[i + 1], wc[j][i + 1]);
+        den[j] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const bool on = e < n[j] && n[j] <= NE;
+            src[j][e] = on ? (unsigned)(key[e] & 0x1fffffff) : 0u;
+            wg[j][e] = 1.0f;
+            if (MODE == DRBA_SPLAT_LINEAR) wg[j][e] = on ? met[src[j][e]] : 0.0f;
+            if (MODE == DRBA_SPLAT_SOFT) wg[j][e] = on ? expf(met[src[j][e]]) : 0.0f;
+            if (MODE != DRBA_SPLAT_SUM) den[j] += wg[j][e] * wc[j][e];
+            if (FAST) wc[j][e] = wg[j][e] * wc[j][e];
+            if (on) {
+                const int sy = (int)(src[j][e] / (unsigned)W), sx = (int)(src[j][e] - (unsigned)sy * (unsigned)W);
+                mnx = min(mnx, sx); mxx = max(mxx, sx); mny = min(mny, sy); mxy = max(mxy, sy);
+            }
+        }
+        rden[j] = 1.0f;
+        if (MODE != DRBA_SPLAT_SUM) { den[j] = splat_den(den[j], eps_mode); if (FAST) rden[j] = 1.0f / den[j]; }
+    }
+    // bounding box of the tile's sources
+    int nloc = 0;
+#pragma unroll
+    for (int j = 0; j < kTPT; ++j) nloc = max(nloc, n[j] <= NE ? n[j] : 0);
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {      // shuffles, not redux.sync: ptxas turns the latter into uniform-datapath
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));      // CREDUX, which faulted (illegal instruction) here
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        nloc = max(nloc, __shfl_xor_sync(0xffffffffu, nloc, o));
+    }
+    const int nmax = nloc;                  // warp-wide maximum list length (<= NE)
+    if ((tid & 31) == 0) {
+        atomicMin(&s_min[0], mnx); atomicMin(&s_min[1], mny);
+        atomicMax(&s_max[0], mxx); atomicMax(&s_max[1], mxy);
+    }
+    __syncthreads();
+    // TMA moves 16-byte units: the box must start on a multiple of four floats in the innermost dimension (an
+    // unaligned start coordinate raised "illegal instruction" on B200)
+    const int bx0 = s_min[0] & ~3, by0 = s_min[1];
+    const bool empty_tile = s_max[0] < s_min[0];
+    int bsel = -1;
+    if (!empty_tile)
+        for (int b = kNumBoxes - 1; b >= 0; --b)
+            if (s_max[0] - bx0 < c_box_w[b] && s_max[1] - by0 < c_box_h[b]) bsel = b;
+    const bool fits = bsel >= 0;
+
+    // sources too spread for the largest box (or none at all): the per-target kernel that runs next serves this tile
+    if (!fits) return;
+    if (tid == 0) done[blockIdx.x] = 1;
+
+    // targets with more than 8 entries (folds) are left to the per-target kernel as well: served here they would
+    // stall the whole tile behind one thread (measured: 39 % of the tiles of a gentle flow hold such targets)
+
+    // ---- staged loop: source offsets relative to the box ---------------------------------------------------------------
+    const int bw = c_box_w[bsel], bh = c_box_h[bsel];
+    const int plane = bh * bw, stage_floats = kBoxC * plane;
+    int nst = kRingBytes / (stage_floats * 4);
+    nst = nst > kMaxBoxStages ? kMaxBoxStages : nst;
+    const CUtensorMap* tmap = &maps.m[bsel];
+    // two 16-bit box offsets per register (box h * w < 65536)
+    unsigned offp[kTPT][NE / 2];
+#pragma unroll
+    for (int j = 0; j < kTPT; ++j)
+#pragma unroll
+        for (int e = 0; e < NE; e += 2) {
+            unsigned o2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int sy = (int)(src[j][e + h] / (unsigned)W), sx = (int)(src[j][e + h] - (unsigned)sy * (unsigned)W);
+                o2[h] = (e + h < n[j] && n[j] <= NE) ? (unsigned)((sy - by0) * bw + (sx - bx0)) : 0u;
+            }
+            offp[j][e / 2] = o2[0] | (o2[1] << 16);
+        }
+    float* outj[kTPT];
+#pragma unroll
+    for (int j = 0; j < kTPT; ++j) outj[j] = out + (size_t)img * C * HW + rp[j];
+
+    const int nchunks = (C + kBoxC - 1) / kBoxC;
+    const int plane0 = img * C;
+    if (tid == 0) {
+        for (int s = 0; s < nst && s < nchunks; ++s) {
+            sg_mbar_expect_tx(&full_bar[s], (uint32_t)(stage_floats * 4));
+            sg_tma_load_3d(sg_smem_u32(sg_box + s * stage_floats), tmap, &full_bar[s], bx0, by0, plane0 + s * kBoxC);
+        }
+    }
+    for (int it = 0; it < nchunks; ++it) {
+        const int s = it % nst;
+        sg_mbar_wait(&full_bar[s], (uint32_t)(it / nst) & 1u);
+        const float* box = sg_box + s * stage_floats;
+        const int c0 = it * kBoxC;
+#pragma unroll
+        for (int j = 0; j < kTPT; ++j) {
+            if (!live[j] || n[j] > NE) continue;
+            float acc[kBoxC];
+#pragma unroll
+            for (int k = 0; k < kBoxC; ++k) acc[k] = 0.0f;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                if (e < nmax) {          // warp-uniform; absent entries carry weight 0 and offset 0
+                    const float* bp = box + ((e & 1) ? (offp[j][e >> 1] >> 16) : (offp[j][e >> 1] & 0xffffu));
+#pragma unroll
+                    for (int k = 0; k < kBoxC; ++k) {
+                        float v = bp[k * plane];
+                        if (FAST) acc[k] = fmaf(v, wc[j][e], acc[k]);
+                        else { if (MODE == DRBA_SPLAT_LINEAR) v = v * wg[j][e]; acc[k] += v * wc[j][e]; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kBoxC; ++k)
+                if (c0 + k < C)
+                    outj[j][(size_t)(c0 + k) * HW] = MODE == DRBA_SPLAT_SUM ? acc[k] : (FAST ? acc[k] * rden[j] : acc[k] / den[j]);
+        }
+        __syncthreads();              // every thread is done with stage s
+        if (tid == 0 && it + nst < nchunks) {
+            sg_mbar_expect_tx(&full_bar[s], (uint32_t)(stage_floats * 4));
+            sg_tma_load_3d(sg_smem_u32(sg_box + s * stage_floats), tmap, &full_bar[s], bx0, by0, plane0 + (it + nst) * kBoxC);
+        }
+    }
+}
+
+typedef CUresult (*SgEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static SgEncodeTiledFn sg_get_encode()
+{
+    static SgEncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<SgEncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
 static GatherWs carve(void* ws, size_t total)
 {
     GatherWs g;
@@ -339,6 +586,9 @@ static GatherWs carve(void* ws, size_t total)
     g.offcnt = reinterpret_cast<int2*>(b);                       b += total4 * sizeof(int2);
     g.entries = reinterpret_cast<int2*>(b);                      b += 4 * total4 * sizeof(int2);
     g.block_sums = reinterpret_cast<int*>(b);
+    const size_t nblocks = (total + kScanBlock - 1) / kScanBlock;
+    b += (nblocks + 4) * sizeof(int);
+    g.done = reinterpret_cast<int*>(b);
     return g;
 }
 
@@ -347,11 +597,12 @@ size_t splat_gather_workspace_bytes(int N, int H, int W)
     const size_t total = (size_t)N * H * W;
     const size_t total4 = (total + 3) / 4 * 4;
     const size_t nblocks = (total + kScanBlock - 1) / kScanBlock;
-    return total4 * 4 + total4 * 8 + 4 * total4 * 8 + (nblocks + 4) * 4;
+    const size_t ntiles = (size_t)N * ((W + 63) / 64) * ((H + 15) / 16);
+    return total4 * 4 + total4 * 8 + 4 * total4 * 8 + (nblocks + 4) * 4 + (ntiles + 4) * 4;
 }
 
 int splat_gather_launch(const float* in, const float* flow, const float* metric, float* out,
-                        int N, int C, int H, int W, int mode, int eps_mode, void* ws, cudaStream_t st)
+                        int N, int C, int H, int W, int mode, int eps_mode, void* ws, cudaStream_t st, bool tile)
 {
     const size_t total = (size_t)N * H * W;
     if (total >= (1ull << 31) || (size_t)H * W >= (1ull << 29) || (size_t)C * H * W >= (1ull << 32)) return DRBA_E_UNSUPPORTED;   // list keys: corner << 29 | pixel index
@@ -368,7 +619,50 @@ int splat_gather_launch(const float* in, const float* flow, const float* metric,
     DRBA_RETURN_IF_LAUNCH_FAILED();
     splat_list_kernel<true><<<grid, kGThreads, 0, st>>>(flow, g.count, g.offcnt, g.entries, N, H, W);
     DRBA_RETURN_IF_LAUNCH_FAILED();
-#define GATHER(M) splat_gather_kernel<M, 8><<<grid, kGThreads, 0, st>>>(in, metric, out, g.offcnt, g.entries, N, C, H, W, eps_mode, env_dbg)
+    // tile flavour (sources staged by TMA) when the tensor can be described by a tiled map: W * 4 bytes a multiple of 16
+    static int env_tile = -1;
+    if (env_tile < 0) { const char* e = getenv("DRBA_SPLAT_TILE"); env_tile = e ? atoi(e) : 1; }
+    const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
+    bool tiled = false;
+    if (env_tile && tile && W % 4 == 0 && (size_t)N * C < (1u << 30) && aligned16(in)) {
+        SgEncodeTiledFn encode = sg_get_encode();
+        BoxMaps maps;
+        bool ok = encode != nullptr;
+        for (int b = 0; ok && b < kNumBoxes; ++b) {
+            const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * C};
+            const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+            const cuuint32_t box[3] = {(cuuint32_t)h_box_w[b], (cuuint32_t)h_box_h[b], kBoxC};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            ok = encode(&maps.m[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        if (ok) {
+            static bool attr = false;
+            const size_t smem = (size_t)kRingBytes;
+            if (!attr) {
+                cudaFuncSetAttribute(splat_gather_tile_kernel<DRBA_SPLAT_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(splat_gather_tile_kernel<DRBA_SPLAT_AVG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(splat_gather_tile_kernel<DRBA_SPLAT_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(splat_gather_tile_kernel<DRBA_SPLAT_SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr = true;
+            }
+            const unsigned tgrid = (unsigned)(N * tiles_x * tiles_y);
+#define GATHER_T(M) splat_gather_tile_kernel<M><<<tgrid, kTileThreads, smem, st>>>(maps, in, metric, out, g.offcnt, g.entries, g.done, N, C, H, W, eps_mode, tiles_x, tiles_y)
+            switch (mode) {
+                case DRBA_SPLAT_SUM: GATHER_T(DRBA_SPLAT_SUM); break;
+                case DRBA_SPLAT_AVG: GATHER_T(DRBA_SPLAT_AVG); break;
+                case DRBA_SPLAT_LINEAR: GATHER_T(DRBA_SPLAT_LINEAR); break;
+                default: GATHER_T(DRBA_SPLAT_SOFT); break;
+            }
+#undef GATHER_T
+            DRBA_RETURN_IF_LAUNCH_FAILED();
+            tiled = true;
+        }
+    }
+    // the per-target kernel serves whatever the tile kernel left (every tile when it did not run)
+    const int* done = tiled ? g.done : nullptr;
+#define GATHER(M) splat_gather_kernel<M, 8><<<grid, kGThreads, 0, st>>>(in, metric, out, g.offcnt, g.entries, N, C, H, W, eps_mode, env_dbg, done, tiles_x, tiles_y)
     switch (mode) {
         case DRBA_SPLAT_SUM: GATHER(DRBA_SPLAT_SUM); break;
         case DRBA_SPLAT_AVG: GATHER(DRBA_SPLAT_AVG); break;
@@ -383,6 +677,10 @@ int splat_gather_launch(const float* in, const float* flow, const float* metric,
     const size_t total4 = (total + 3) / 4 * 4;
     const cudaError_t me = cudaMemsetAsync(g.offcnt, 0, total4 * sizeof(int2) + 4 * total4 * sizeof(int2), st);
     if (me != cudaSuccess) return (int)me;
+    if (tiled) {
+        const cudaError_t me2 = cudaMemsetAsync(g.done, 0, (size_t)N * tiles_x * tiles_y * sizeof(int), st);
+        if (me2 != cudaSuccess) return (int)me2;
+    }
     return DRBA_OK;
 }
 

@@ -17,8 +17,10 @@ Differences a caller can observe (DESIGN.md "boundary"):
   ``reuse``) is captured once into a CUDA graph and replayed, which removes the ~150 kernel-launch
   gaps per window.  Replays read static input buffers (inputs are copied in) and the returned
   frames are copies of the graph's output buffers; the returned ``reuse`` tuple aliases graph
-  buffers that stay valid until the same window shape runs again (infer.py consumes it in the
-  very next window).
+  buffers that are valid for the NEXT call (infer.py consumes it in the very next window; graphs
+  share one memory pool).  Window shapes whose input ADDRESSES recur (a frame ring, and ``reuse``
+  coming straight from the previous graph) are replayed from graphs captured on those addresses:
+  no input copies at all.
 """
 import os
 
@@ -63,7 +65,10 @@ class RIFE:
         self.scale_list = [16 / scale, 8 / scale, 4 / scale, 2 / scale, 1 / scale]
         self.pad_size = 64
         self.graphs = bool(graphs)
+        self.address_graphs = os.environ.get("DRBA_ADDRESS_GRAPHS", "1") != "0"
         self._graphs = {}
+        self._agraphs, self._aseen, self._pool = {}, {}, None
+        self.captures = 0          # graphs captured so far (a driver can warm up until this stops growing)
         self._capture_stream = None
 
     @torch.inference_mode()
@@ -98,6 +103,27 @@ class RIFE:
             return self._drba_graphed(I0, I1, I2, ts, reuse, linear)
         return self._drba_eager(I0, I1, I2, ts, reuse, linear)
 
+    # ---- address-keyed graphs ----------------------------------------------------------------------------------
+    # The generic graph of a window shape reads static input buffers: every window copies three frames (75 MB at
+    # 1080p) and the `reuse` tuple (167 MB) into them.  A driver loop hands the same few buffers round and round (a
+    # frame ring, and `reuse` = the previous graph's own output buffers), so a window whose (shape, timestamps, input
+    # ADDRESSES) combination has been seen before gets a graph captured directly on those addresses: a replay reads
+    # whatever the caller's tensors hold now -- no copies, no staleness (a key only matches while live tensors of
+    # the same shape and dtype sit at those addresses).  All graphs share one memory pool.
+    MAX_ADDRESS_GRAPHS = 64
+
+    def _address_key(self, key, frames, reuse):
+        for f in frames:
+            if f.dtype != torch.float32 or not f.is_contiguous():
+                return None
+        k = key + tuple(f.data_ptr() for f in frames)
+        if reuse:
+            for r in reuse:
+                if not torch.is_tensor(r):
+                    return None
+                k += (r.data_ptr(), r.dtype, tuple(r.shape), tuple(r.stride()))
+        return k
+
     def _drba_graphed(self, I0, I1, I2, ts, reuse, linear):
         ts_key = tuple(float(t) for t in ts)
         frames = (I0, I1, I2)
@@ -105,6 +131,22 @@ class RIFE:
             if not f.is_cuda:
                 raise _lib.DrbaError("drba_b200.RIFE runs on CUDA tensors only (no CPU fallback)")
         key = (tuple(I0.shape), ts_key, bool(reuse), bool(linear))
+        akey = self._address_key(key, frames, reuse) if self.address_graphs else None
+        if akey is not None:
+            hit = self._agraphs.get(akey)
+            if hit is None:
+                seen = self._aseen.get(akey, 0) + 1
+                self._aseen[akey] = seen
+                if seen >= 2 and len(self._agraphs) < self.MAX_ADDRESS_GRAPHS:
+                    hit = self._capture_on_addresses(akey, frames, ts, reuse, linear)
+                elif len(self._aseen) > 4096:
+                    self._aseen.clear()
+            if hit is not None:
+                graph, outs, new_reuse, passthrough, n_kernels = hit
+                graph.replay()
+                _lib.count(n_kernels)
+                _lib.check_async("RIFE window graph")
+                return [frames[pt] if pt >= 0 else o.clone() for o, pt in zip(outs, passthrough)], new_reuse
         entry = self._graphs.get(key)
         if entry is None:
             entry = self._capture(key, frames, ts, reuse, linear)
@@ -134,6 +176,32 @@ class RIFE:
             output.append(frames[pt] if pt >= 0 else o.clone())   # t in {0,1,2}: the input tensor itself (rife.py:89-94)
         return output, new_reuse
 
+    def _capture_on_addresses(self, akey, frames, ts, reuse, linear):
+        """Capture this window on the caller's own tensors (see above)."""
+        dev = self.device
+        if self._capture_stream is None:
+            self._capture_stream = torch.cuda.Stream(device=dev)
+        cs = self._capture_stream
+        r = tuple(reuse) if reuse else None
+        cs.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cs):      # warm-up: allocates engine buffers / workspaces outside the capture
+            self._drba_eager(*frames, ts, r, linear)
+        torch.cuda.current_stream(dev).wait_stream(cs)
+        torch.cuda.synchronize(dev)
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        graph = torch.cuda.CUDAGraph()
+        k0 = _lib.KERNEL_LAUNCHES
+        with torch.cuda.graph(graph, stream=cs, pool=self._pool):
+            outs, new_reuse = self._drba_eager(*frames, ts, r, linear)
+        n_kernels = _lib.KERNEL_LAUNCHES - k0
+        _lib.count(-n_kernels)     # capture records, it does not execute
+        passthrough = [next((k for k, f in enumerate(frames) if o is f), -1) for o in outs]
+        hit = (graph, outs, new_reuse, passthrough, n_kernels)
+        self._agraphs[akey] = hit
+        self.captures += 1
+        return hit
+
     def _capture(self, key, frames, ts, reuse, linear):
         dev = self.device
         s_in = [torch.empty_like(f, dtype=torch.float32, memory_format=torch.contiguous_format) for f in frames]
@@ -162,6 +230,7 @@ class RIFE:
             passthrough.append(next((k for k, si in enumerate(s_in) if o is si), -1))
         entry = (s_in, s_reuse, graph, outs, new_reuse, passthrough, n_kernels)
         self._graphs[key] = entry
+        self.captures += 1
         return entry
 
     def _drba_eager(self, I0, I1, I2, ts, reuse=None, linear=False):

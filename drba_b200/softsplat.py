@@ -48,7 +48,7 @@ def softsplat(tenIn, tenFlow, tenMetric, strMode: str, _variant=0):
     out = torch.empty_like(x)
     L = _lib.lib()
     with torch.cuda.device(x.device):
-        need = L.drba_softsplat_workspace_bytes(n, c if _variant != 3 else max(c, 16), h, w, mode)
+        need = L.drba_softsplat_workspace_bytes(n, c if _variant not in (3, 4) else max(c, 16), h, w, mode)
         ws = Workspace.get(need, x.device)
         group_bytes = n * h * w * 16
         has_w = 0 if mode == 0 else 1

@@ -281,12 +281,14 @@ def test_frame_io_roundtrip():
         assert int(d.min()) >= 0 and int(d.max()) <= 1
 
 
+@pytest.mark.parametrize("variant", [3, 4])
 @pytest.mark.parametrize("mode", ["sum", "avg", "linear", "soft", "avg-zeroeps", "soft-clipeps"])
-@pytest.mark.parametrize("shape", [(1, 1, 64, 96), (2, 12, 33, 47), (1, 64, 40, 56), (1, 19, 128, 160)])
-def test_softsplat_gather_path_bit_exact_vs_oracle(mode, shape):
-    """Owner-computes path (csrc/splat_gather.cu, variant 3): sums in ascending source order like the
-    sequential CPU restatement -> bit-identical for sum / avg / linear; `soft` differs through expf only.
-    Includes a region where > 12 sources land on one target (slow path) and checks the workspace is zero."""
+@pytest.mark.parametrize("shape", [(1, 1, 64, 96), (2, 12, 33, 47), (1, 64, 40, 56), (1, 19, 128, 160), (2, 9, 48, 200)])
+def test_softsplat_gather_path_bit_exact_vs_oracle(mode, shape, variant):
+    """Owner-computes path (csrc/splat_gather.cu; variant 3: per-target loads, variant 4: source tiles staged in shared
+    memory by TMA): sums in ascending source order like the sequential CPU restatement -> bit-identical for sum / avg /
+    linear; `soft` differs through expf only.  Includes a region where > 12 sources land on one target (slow path),
+    tiles whose sources do not fit the staging box, and checks the workspace is zero."""
     from drba_b200._torch_util import Workspace
     from drba_b200.softsplat import softsplat
     rng = np.random.default_rng(abs(hash((mode, shape))) % (2 ** 32))
@@ -304,8 +306,8 @@ def test_softsplat_gather_path_bit_exact_vs_oracle(mode, shape):
     if base == "linear":
         metric = np.abs(metric) + 0.1
     want = cport.softsplat(x, flow, metric, mode)
-    got_t = softsplat(cu(x), cu(flow), cu(metric), mode, _variant=3)
-    again = softsplat(cu(x), cu(flow), cu(metric), mode, _variant=3)
+    got_t = softsplat(cu(x), cu(flow), cu(metric), mode, _variant=variant)
+    again = softsplat(cu(x), cu(flow), cu(metric), mode, _variant=variant)
     got = got_t.cpu().numpy()
     assert np.array_equal(got, again.cpu().numpy(), equal_nan=True), "gather path must be run-to-run deterministic"
     if base == "soft":
@@ -364,3 +366,23 @@ def test_softsplat_unknown_suffix_no_eps(variant):
         want = d[key]
         np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
         np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(want), rtol=1e-4, atol=1e-4 * float(np.nanmax(np.abs(want))))
+
+
+@pytest.mark.parametrize("mode", ["avg", "soft"])
+def test_softsplat_tile_path_full_size_equals_per_target_path(mode):
+    """C = 64 at 1152 x 1920 (the size of bench.py's softsplat_roofline): the TMA-staged tile kernel (variant 4) must
+    give bit for bit what the per-target gather (variant 3) gives -- same lists, same order, same arithmetic -- on a
+    gentle flow (every tile takes the staged path) with a fold region and a fast-moving patch (tiles that do not fit)."""
+    from drba_b200.softsplat import softsplat
+    c, h, w = 64, 1152, 1920
+    g = torch.Generator(device="cpu").manual_seed(4)
+    lo = 2.0 * torch.randn((1, 2, h // 16, w // 16), generator=g)
+    flow = (torch.nn.functional.interpolate(lo, size=(h, w), mode="bilinear", align_corners=False) + 6.5).cuda()
+    flow[:, :, 200:264, 300:428] += 40.0 * torch.randn((1, 2, 64, 128), generator=g).cuda()      # folds
+    flow[:, 0, 600:700, 900:1100] += 300.0                                                          # far away sources
+    x = torch.randn((1, c, h, w), generator=g).cuda()
+    metric = None if mode == "avg" else (0.5 * torch.randn((1, 1, h, w), generator=g)).cuda()
+    a = softsplat(x, flow, metric, mode, _variant=3)
+    b = softsplat(x, flow, metric, mode, _variant=4)
+    d = softsplat(x, flow, metric, mode)                   # the default picks the tile path
+    assert torch.equal(a, b) and torch.equal(a, d)
