@@ -72,6 +72,8 @@ SIGNATURES = {
     "drba_check_scene_f32": (_I, [_P, _P, _c.c_longlong, _c.c_longlong, _I, _I, _I, _F, _P, _P, _P]),
     "drba_ifnet_assemble": (_I, [_P, _P, _P, _P, _I, _P, _F, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P]),
     "drba_ifnet_flow_accum": (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _P]),
+    "drba_ifnet_assemble_terms": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "drba_ifnet_flow_sum": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P]),
     "drba_ifnet_blend": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P]),
 }
 

@@ -330,13 +330,23 @@ conv_tc_kernel(const __grid_constant__ Program prog)
     const int nlayers = prog.nlayers;
 
     // bias / PReLU slopes of the current layer live in shared memory (the epilogue reads them per tile)
+    // Executed by warps 1.. only: thread 0 goes straight from the layer boundary into the grid barrier (its share of
+    // the table loads used to sit on every CTA's critical path after the barrier).  The same threads touch the next
+    // layer's descriptor in the constant bank (kernel parameters), so that the ~25 scalar reads at the top of the
+    // layer loop hit the constant cache instead of missing one after the other behind the barrier.
     auto stage_tables = [&](int li) {
         const LayerDev& L = prog.L[li];
         const int nb = L.G * L.cout_pad;
+        const int t = (int)threadIdx.x - 32;
+        if (t < 0) return;
         if (L.has_bias)
-            for (int i = threadIdx.x; i < nb; i += kTcThreads) s_bias[i] = L.bias[i];
+            for (int i = t; i < nb; i += kTcThreads - 32) s_bias[i] = L.bias[i];
         if (L.act == 2)
-            for (int i = threadIdx.x; i < L.cout_pad; i += kTcThreads) s_slope[i] = L.slope[i];
+            for (int i = t; i < L.cout_pad; i += kTcThreads - 32) s_slope[i] = L.slope[i];
+        if (t < (int)(sizeof(LayerDev) / 32)) {
+            const int v = reinterpret_cast<const int*>(&L)[t * 8];
+            asm volatile("" ::"r"(v));                       // keeps the (constant-bank) read alive
+        }
     };
     uint32_t bprod_uses = 0;         // weight producer warp: resident layers issued so far
     // resident mode: every weight tile of the layer, once (B producer warp, warp-converged)

@@ -50,6 +50,32 @@ ifnet_flow_accum_kernel(const Tmp13 t, float* __restrict__ flow, float* __restri
     }
 }
 
+// flow = s0 * up(tmp0) + s1 * up(tmp1) + s2 * up(tmp2), summed in block order: what three consecutive
+// ifnet_flow_accum launches leave behind, in ONE write-only pass (the coarse blocks' assemble kernels evaluate
+// the flow at their own sample positions, so the first full-resolution flow is needed before block 3 only)
+__global__ void __launch_bounds__(256)
+ifnet_flow_sum_kernel(const Tmp13 t0, const Tmp13 t1, const Tmp13 t2, int nterms, float* __restrict__ flow, int H, int W)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= H * W) return;
+    const int y = idx / W, x = idx - y * W;
+    float o[4];
+    up_tmp<1, 0, 4>(t0, y, x, o);
+    float fs = (float)t0.s;
+    float4 f = make_float4(o[0] * fs, o[1] * fs, o[2] * fs, o[3] * fs);
+    if (nterms > 1) {
+        up_tmp<1, 0, 4>(t1, y, x, o);
+        fs = (float)t1.s;
+        f.x = f.x + o[0] * fs; f.y = f.y + o[1] * fs; f.z = f.z + o[2] * fs; f.w = f.w + o[3] * fs;
+    }
+    if (nterms > 2) {
+        up_tmp<1, 0, 4>(t2, y, x, o);
+        fs = (float)t2.s;
+        f.x = f.x + o[0] * fs; f.y = f.y + o[1] * fs; f.z = f.z + o[2] * fs; f.w = f.w + o[3] * fs;
+    }
+    reinterpret_cast<float4*>(flow)[idx] = f;
+}
+
 // ---- block input assembly ---------------------------------------------------------------
 // Mean of the (up to) 4 sampled positions in the order bilinear resampling adds them:
 // 0.5*(0.5*a + 0.5*b) + 0.5*(0.5*c + 0.5*d) == ((a + b) + (c + d)) * 0.25 exactly in fp32.
@@ -233,18 +259,69 @@ static int tmp_ok(const float* tmp, int layout, int H, int W, int s)
 
 extern "C" {
 
+static int assemble_impl(const float* img0, const float* img1, const void* f0, const void* f1, int feat_dtype,
+                         const float* timestep, float timestep_scalar,
+                         const float* flow, const float* tmp_prev, int tmp_layout, int s_prev,
+                         void* out, int out_dtype, int out_cstride, int H, int W, int s, void* stream,
+                         const float* term0, int s_term0, const float* term1, int s_term1);
+
 int drba_ifnet_assemble(const float* img0, const float* img1, const void* f0, const void* f1, int feat_dtype,
                         const float* timestep, float timestep_scalar,
                         const float* flow, const float* tmp_prev, int tmp_layout, int s_prev,
                         void* out, int out_dtype, int out_cstride, int H, int W, int s, void* stream)
 {
+    return assemble_impl(img0, img1, f0, f1, feat_dtype, timestep, timestep_scalar, flow, tmp_prev, tmp_layout, s_prev,
+                         out, out_dtype, out_cstride, H, W, s, stream, nullptr, 0, nullptr, 0);
+}
+
+int drba_ifnet_assemble_terms(const float* img0, const float* img1, const void* f0, const void* f1,
+                              const float* timestep, float timestep_scalar,
+                              const float* term0, int s_term0, const float* term1, int s_term1,
+                              const float* tmp_prev, int s_prev, void* out, int H, int W, int s, void* stream)
+{
+    if (!term0 || s_term0 <= 0 || (term1 && s_term1 <= 0)) return DRBA_E_ARG;
+    int rc = tmp_ok(term0, 1, H, W, s_term0);
+    if (rc == DRBA_OK && term1) rc = tmp_ok(term1, 1, H, W, s_term1);
+    if (rc != DRBA_OK) return rc;
+    return assemble_impl(img0, img1, f0, f1, DRBA_F16, timestep, timestep_scalar, nullptr, tmp_prev, 1, s_prev,
+                         out, DRBA_F16, 64, H, W, s, stream, term0, s_term0, term1, s_term1);
+}
+
+int drba_ifnet_flow_sum(const float* tmp0, int s0, const float* tmp1, int s1, const float* tmp2, int s2, int nterms,
+                        float* flow, int H, int W, void* stream)
+{
+    if (H <= 0 || W <= 0 || !flow || nterms < 1 || nterms > 3) return DRBA_E_ARG;
+    if (!aligned16(flow)) return DRBA_E_ALIGN;
+    const float* tp[3] = {tmp0, tmp1, tmp2};
+    const int ss[3] = {s0, s1, s2};
+    Tmp13 t[3];
+    for (int k = 0; k < 3; ++k) {
+        t[k].p = tp[0]; t[k].s = 1; t[k].h13 = H; t[k].w13 = W; t[k].pitch = 16;
+        if (k < nterms) {
+            const int rc = tmp_ok(tp[k], 1, H, W, ss[k]);
+            if (rc != DRBA_OK) return rc;
+            t[k].p = tp[k]; t[k].s = ss[k]; t[k].h13 = H / ss[k]; t[k].w13 = W / ss[k];
+        }
+    }
+    ifnet_flow_sum_kernel<<<cdiv((size_t)H * W, 256), 256, 0, as_stream(stream)>>>(t[0], t[1], t[2], nterms, flow, H, W);
+    DRBA_RETURN_IF_LAUNCH_FAILED();
+    return DRBA_OK;
+}
+
+static int assemble_impl(const float* img0, const float* img1, const void* f0, const void* f1, int feat_dtype,
+                         const float* timestep, float timestep_scalar,
+                         const float* flow, const float* tmp_prev, int tmp_layout, int s_prev,
+                         void* out, int out_dtype, int out_cstride, int H, int W, int s, void* stream,
+                         const float* term0, int s_term0, const float* term1, int s_term1)
+{
     if (H <= 0 || W <= 0 || s <= 0 || (s & (s - 1)) != 0 || H % s != 0 || W % s != 0) return DRBA_E_ARG;
     if (!img0 || !img1 || !f0 || !f1 || !out) return DRBA_E_ARG;
     if (feat_dtype != DRBA_F32 && feat_dtype != DRBA_F16) return DRBA_E_ARG;
     if (out_dtype != DRBA_F32 && out_dtype != DRBA_F16) return DRBA_E_ARG;
-    if (out_dtype == DRBA_F16 && (out_cstride < (flow ? 64 : 48) || out_cstride % 8 != 0)) return DRBA_E_ARG;
+    const bool has_flow = flow != nullptr || term0 != nullptr;
+    if (out_dtype == DRBA_F16 && (out_cstride < (has_flow ? 64 : 48) || out_cstride % 8 != 0)) return DRBA_E_ARG;
     if (!aligned16(f0) || !aligned16(f1) || !aligned16(out) || (flow && !aligned16(flow))) return DRBA_E_ALIGN;
-    if (flow) {
+    if (has_flow) {
         if (tmp_layout == 2) return DRBA_E_ARG;       // the 8-channel form carries flow + mask only
         const int rc = tmp_ok(tmp_prev, tmp_layout, H, W, s_prev);
         if (rc != DRBA_OK) return rc;
@@ -252,16 +329,20 @@ int drba_ifnet_assemble(const float* img0, const float* img1, const void* f0, co
     AssembleParams p;
     p.img0 = img0; p.img1 = img1; p.f0 = f0; p.f1 = f1;
     p.timestep = timestep; p.timestep_scalar = timestep_scalar; p.flow = flow;
-    p.prev.p = tmp_prev; p.prev.s = flow ? s_prev : 1; p.prev.h13 = flow ? H / s_prev : 1; p.prev.w13 = flow ? W / s_prev : 1; p.prev.pitch = 16;
+    p.prev.p = tmp_prev; p.prev.s = has_flow ? s_prev : 1; p.prev.h13 = has_flow ? H / s_prev : 1; p.prev.w13 = has_flow ? W / s_prev : 1; p.prev.pitch = 16;
+    p.nfterms = term0 ? (term1 ? 2 : 1) : 0;
+    p.fterm[0].p = term0; p.fterm[0].s = term0 ? s_term0 : 1; p.fterm[0].h13 = term0 ? H / s_term0 : 1; p.fterm[0].w13 = term0 ? W / s_term0 : 1; p.fterm[0].pitch = 16;
+    p.fterm[1].p = term1; p.fterm[1].s = term1 ? s_term1 : 1; p.fterm[1].h13 = term1 ? H / s_term1 : 1; p.fterm[1].w13 = term1 ? W / s_term1 : 1; p.fterm[1].pitch = 16;
     p.out = out; p.out_cstride = out_cstride; p.H = H; p.W = W; p.s = s; p.h = H / s; p.w = W / s;
     const unsigned grid = cdiv((size_t)p.h * p.w, 32);
     cudaStream_t st = as_stream(stream);
     const int key = (feat_dtype == DRBA_F16 ? 4 : 0) | (out_dtype == DRBA_F16 ? 2 : 0) | (tmp_layout == 1 ? 1 : 0);
-    if (key == 7 && flow && out_cstride == 64 && !env_flag("DRBA_ASSEMBLE_V1")) {
+    if (key == 7 && has_flow && out_cstride == 64 && (term0 || !env_flag("DRBA_ASSEMBLE_V1"))) {
         launch_assemble_tc(p, st);
         DRBA_RETURN_IF_LAUNCH_FAILED();
         return DRBA_OK;
     }
+    if (term0) return DRBA_E_UNSUPPORTED;      // flow terms: tensor-core engine layout only
     switch (key) {
         case 0: ifnet_assemble_kernel<float, false, 0><<<grid, kIfThreads, 0, st>>>(p); break;
         case 1: ifnet_assemble_kernel<float, false, 1><<<grid, kIfThreads, 0, st>>>(p); break;

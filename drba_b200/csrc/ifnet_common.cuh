@@ -165,9 +165,30 @@ struct AssembleParams {
     const float* timestep; float timestep_scalar;   // [H][W] or NULL -> scalar
     const float* flow;                      // [H][W][4] fp32 state, or NULL (first block: no warp, 39 channels)
     Tmp13 prev;                             // previous block's lastconv output (mask/feat source)
+    Tmp13 fterm[2]; int nfterms;            // flow given as a SUM of up-sampled lastconv outputs (flow == NULL): coarse blocks
+                                            // sample 1/16 or 1/4 of the pixels, so the full-resolution flow state is not
+                                            // materialised for them (load_flow below)
     void* out; int out_cstride;             // NHWC: channels allocated per pixel
     int H, W, s, h, w;                      // full size, integer scale, h = H/s, w = W/s
 };
+
+// flow at (y, x): the materialised state, or s0 * up(tmp0)[0:4] (+ s1 * up(tmp1)[0:4]) in the order
+// ifnet_flow_accum_kernel accumulates them (IFNet_HDv3.py:91-93, :157)
+template <int TMP_LAYOUT>
+__device__ __forceinline__ float4 load_flow(const AssembleParams& p, int y, int x)
+{
+    if (p.nfterms == 0) return reinterpret_cast<const float4*>(p.flow)[(size_t)y * p.W + x];
+    float o[4];
+    up_tmp<TMP_LAYOUT, 0, 4>(p.fterm[0], y, x, o);
+    float fs = (float)p.fterm[0].s;
+    float4 f = make_float4(o[0] * fs, o[1] * fs, o[2] * fs, o[3] * fs);
+    if (p.nfterms > 1) {
+        up_tmp<TMP_LAYOUT, 0, 4>(p.fterm[1], y, x, o);
+        fs = (float)p.fterm[1].s;
+        f.x = f.x + o[0] * fs; f.y = f.y + o[1] * fs; f.z = f.z + o[2] * fs; f.w = f.w + o[3] * fs;
+    }
+    return f;
+}
 
 // ifnet_tc.cu: the L1-friendly NHWC fp16 kernel
 void launch_assemble_tc(const AssembleParams& p, cudaStream_t st);

@@ -66,7 +66,6 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
     const int base = blockIdx.x * kAsmTile;
     const int off = NP == 1 ? 0 : p.s / 2 - 1;
     const size_t HW = (size_t)p.H * p.W;
-    const float4* flow4 = reinterpret_cast<const float4*>(p.flow);
     constexpr int PXW = NP == 1 ? 16 : 8;      // output pixels per warp pass
 
     if (role < 2) {
@@ -82,13 +81,13 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
             const int x = p.s * X + off + xpos, y = p.s * Y + off;
             float r0[8];
             {
-                const float4 fl = flow4[(size_t)y * p.W + x];
+                const float4 fl = load_flow<1>(p, y, x);
                 const WarpTap t = warp_tap(x, y, role == 0 ? fl.x : fl.z, role == 0 ? fl.y : fl.w, p.H, p.W);
                 sample_feat8(f, t, r0);
             }
             if (NP == 4) {
                 float r1[8];
-                const float4 fl = flow4[(size_t)(y + 1) * p.W + x];
+                const float4 fl = load_flow<1>(p, y + 1, x);
                 const WarpTap t = warp_tap(x, y + 1, role == 0 ? fl.x : fl.z, role == 0 ? fl.y : fl.w, p.H, p.W);
                 sample_feat8(f, t, r1);
 #pragma unroll
@@ -114,14 +113,14 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
             const int x = p.s * X + off + xpos, y = p.s * Y + off;
             float r0[3];
             {
-                const float4 fl = flow4[(size_t)y * p.W + x];
+                const float4 fl = load_flow<1>(p, y, x);
                 const WarpTap t = warp_tap(x, y, sel ? fl.z : fl.x, sel ? fl.w : fl.y, p.H, p.W);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) r0[c] = sample_plane(img + (size_t)c * HW, t);
             }
             if (NP == 4) {
                 float r1[3];
-                const float4 fl = flow4[(size_t)(y + 1) * p.W + x];
+                const float4 fl = load_flow<1>(p, y + 1, x);
                 const WarpTap t = warp_tap(x, y + 1, sel ? fl.z : fl.x, sel ? fl.w : fl.y, p.H, p.W);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) r1[c] = sample_plane(img + (size_t)c * HW, t);
@@ -154,7 +153,7 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
             const int Y = idx / p.w, X = idx - Y * p.w;
             const int x = p.s * X + off + (K & 1), y = p.s * Y + off + (K >> 1);
             float v[16];
-            const float4 fl = flow4[(size_t)y * p.W + x];
+            const float4 fl = load_flow<1>(p, y, x);
             v[0] = p.timestep ? p.timestep[(size_t)y * p.W + x] : p.timestep_scalar;
             up_tmp<1, 4, 9>(p.prev, y, x, v + 1);
             v[10] = fl.x; v[11] = fl.y; v[12] = fl.z; v[13] = fl.w;

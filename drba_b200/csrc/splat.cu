@@ -295,12 +295,12 @@ int drba_softsplat_f32_variant(const float* in, const float* flow, const float* 
     if (!aligned16(ws)) return DRBA_E_ALIGN;
     const int has_w = mode != DRBA_SPLAT_SUM ? 1 : 0;
     // variant: 0 = automatic, 1 = scalar atomics (the reference kernel's scheme), 2 = vector-red scatter,
-    //          3 = owner-computes gather, per-target loads (csrc/splat_gather.cu), 4 = the same with TMA-staged
-    //          source tiles (what variant 0 picks for C + weight >= 9)
+    //          3 = owner-computes gather, per-target loads (csrc/splat_gather.cu; what variant 0 picks for
+    //          C + weight >= 9), 4 = the same with TMA-staged source tiles (measured slower on B200: kept selectable)
     if (variant == 3 || variant == 4 || (variant == 0 && C + has_w >= kGatherMinChannels)) {
         const size_t need = splat_gather_workspace_bytes(N, H, W);
         if (ws_bytes >= need) {
-            const int rc = splat_gather_launch(in, flow, metric, out, N, C, H, W, mode, eps_mode, ws, as_stream(stream), variant != 3);
+            const int rc = splat_gather_launch(in, flow, metric, out, N, C, H, W, mode, eps_mode, ws, as_stream(stream), variant == 4);
             if (rc != DRBA_E_UNSUPPORTED) return rc;
         } else if (variant == 3 || variant == 4) {
             return DRBA_E_WORKSPACE;

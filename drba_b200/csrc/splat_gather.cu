@@ -253,20 +253,21 @@ splat_gather_kernel(const float* __restrict__ in, const float* __restrict__ metr
                     float* __restrict__ out, int2* __restrict__ offcnt, int2* __restrict__ entries,
                     int N, int C, int H, int W, int eps_mode, int dbg, const int* __restrict__ done, int tiles_x, int tiles_y)
 {
+    // CTA = 32 x 8 targets (a warp = 32 x-adjacent targets of one row; the eight rows of a CTA share their source rows
+    // in L1), grid = (tiles per image, N)
     const size_t HW = (size_t)H * W;
-    const size_t p = (size_t)blockIdx.x * kGThreads + threadIdx.x;
-    bool live = p < (size_t)N * HW;
+    const int img = blockIdx.y;
+    const int gtx = (W + 31) >> 5;
+    const int ty = blockIdx.x / gtx, tx = blockIdx.x - ty * gtx;
+    const int x = tx * 32 + (threadIdx.x & 31), y = ty * 8 + (threadIdx.x >> 5);
+    bool live = x < W && y < H;
+    const size_t rp = live ? (size_t)y * W + x : 0;
+    const size_t p = (size_t)img * HW + rp;
     if (done && live) {
         // tiles already served by splat_gather_tile_kernel (64 x 16 targets, see below) -- except their targets with
         // more than 8 entries, which that kernel leaves to this one
-        const int im = (int)(p / HW);
-        const size_t r = p - (size_t)im * HW;
-        const int y = (int)(r / W), x = (int)(r - (size_t)y * W);
-        if (done[(im * tiles_y + (y >> 4)) * tiles_x + (x >> 6)] && offcnt[p].y <= 8) live = false;
+        if (done[(img * tiles_y + (y >> 4)) * tiles_x + (x >> 6)] && offcnt[p].y <= 8) live = false;
     }
-    const size_t pc = live ? p : 0;
-    const int img = (int)(pc / HW);
-    const size_t rp = pc - (size_t)img * HW;
     int2 oc = make_int2(0, 0);
     if (live) oc = offcnt[p];
     const int n = oc.y;
@@ -386,6 +387,76 @@ __device__ __forceinline__ void sg_tma_load_3d(uint32_t dst, const CUtensorMap* 
                  ::"r"(dst), "l"(map), "r"(sg_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+template <int MODE, int BW, int BH>
+__device__ __forceinline__ void staged_loop(const CUtensorMap* tmap, float* sg_box, uint64_t* full_bar,
+                                            const unsigned (&src)[kTPT][8], const float (&wc)[kTPT][8], const float (&wg)[kTPT][8],
+                                            const float (&den)[kTPT], const float (&rden)[kTPT], const int (&n)[kTPT],
+                                            const bool (&live)[kTPT], const unsigned (&rp)[kTPT], float* outb, int nmax,
+                                            int bx0, int by0, int plane0, int C, int W, size_t HW)
+{
+    constexpr int NE = 8;
+    constexpr bool FAST = MODE == DRBA_SPLAT_SOFT;
+    constexpr int plane = BH * BW, stage_floats = kBoxC * plane;
+    constexpr int nst = kRingBytes / (stage_floats * 4) > kMaxBoxStages ? kMaxBoxStages : kRingBytes / (stage_floats * 4);
+    const int tid = threadIdx.x;
+    // two 16-bit byte offsets into the box per register (BH * BW * 4 < 65536)
+    unsigned offp[kTPT][NE / 2];
+#pragma unroll
+    for (int j = 0; j < kTPT; ++j)
+#pragma unroll
+        for (int e = 0; e < NE; e += 2) {
+            unsigned o2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int sy = (int)(src[j][e + h] / (unsigned)W), sx = (int)(src[j][e + h] - (unsigned)sy * (unsigned)W);
+                o2[h] = (e + h < n[j] && n[j] <= NE) ? (unsigned)(((sy - by0) * BW + (sx - bx0)) * 4) : 0u;
+            }
+            offp[j][e / 2] = o2[0] | (o2[1] << 16);
+        }
+    const int nchunks = (C + kBoxC - 1) / kBoxC;
+    if (tid == 0) {
+        for (int s = 0; s < nst && s < nchunks; ++s) {
+            sg_mbar_expect_tx(&full_bar[s], (uint32_t)(stage_floats * 4));
+            sg_tma_load_3d(sg_smem_u32(sg_box + s * stage_floats), tmap, &full_bar[s], bx0, by0, plane0 + s * kBoxC);
+        }
+    }
+    for (int it = 0; it < nchunks; ++it) {
+        const int s = it % nst;
+        sg_mbar_wait(&full_bar[s], (uint32_t)(it / nst) & 1u);
+        const char* box = reinterpret_cast<const char*>(sg_box + s * stage_floats);
+        const int c0 = it * kBoxC;
+#pragma unroll
+        for (int j = 0; j < kTPT; ++j) {
+            if (!live[j] || n[j] > NE) continue;
+            float acc[kBoxC];
+#pragma unroll
+            for (int k = 0; k < kBoxC; ++k) acc[k] = 0.0f;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                if (e < nmax) {          // warp-uniform; absent entries carry weight 0 and offset 0
+                    const float* bp = reinterpret_cast<const float*>(box + ((e & 1) ? (offp[j][e >> 1] >> 16) : (offp[j][e >> 1] & 0xffffu)));
+#pragma unroll
+                    for (int k = 0; k < kBoxC; ++k) {
+                        float v = bp[k * plane];
+                        if (FAST) acc[k] = fmaf(v, wc[j][e], acc[k]);
+                        else { if (MODE == DRBA_SPLAT_LINEAR) v = v * wg[j][e]; acc[k] += v * wc[j][e]; }
+                    }
+                }
+            }
+            float* o = outb + (size_t)c0 * HW + rp[j];
+#pragma unroll
+            for (int k = 0; k < kBoxC; ++k)
+                if (c0 + k < C)
+                    o[(size_t)k * HW] = MODE == DRBA_SPLAT_SUM ? acc[k] : (FAST ? acc[k] * rden[j] : acc[k] / den[j]);
+        }
+        __syncthreads();              // every thread is done with stage s
+        if (tid == 0 && it + nst < nchunks) {
+            sg_mbar_expect_tx(&full_bar[s], (uint32_t)(stage_floats * 4));
+            sg_tma_load_3d(sg_smem_u32(sg_box + s * stage_floats), tmap, &full_bar[s], bx0, by0, plane0 + (it + nst) * kBoxC);
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kTileThreads, 2)
 splat_gather_tile_kernel(const __grid_constant__ BoxMaps maps, const float* __restrict__ in, const float* __restrict__ metric,
@@ -492,71 +563,13 @@ splat_gather_tile_kernel(const __grid_constant__ BoxMaps maps, const float* __re
     // targets with more than 8 entries (folds) are left to the per-target kernel as well: served here they would
     // stall the whole tile behind one thread (measured: 39 % of the tiles of a gentle flow hold such targets)
 
-    // ---- staged loop: source offsets relative to the box ---------------------------------------------------------------
-    const int bw = c_box_w[bsel], bh = c_box_h[bsel];
-    const int plane = bh * bw, stage_floats = kBoxC * plane;
-    int nst = kRingBytes / (stage_floats * 4);
-    nst = nst > kMaxBoxStages ? kMaxBoxStages : nst;
-    const CUtensorMap* tmap = &maps.m[bsel];
-    // two 16-bit box offsets per register (box h * w < 65536)
-    unsigned offp[kTPT][NE / 2];
-#pragma unroll
-    for (int j = 0; j < kTPT; ++j)
-#pragma unroll
-        for (int e = 0; e < NE; e += 2) {
-            unsigned o2[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int sy = (int)(src[j][e + h] / (unsigned)W), sx = (int)(src[j][e + h] - (unsigned)sy * (unsigned)W);
-                o2[h] = (e + h < n[j] && n[j] <= NE) ? (unsigned)((sy - by0) * bw + (sx - bx0)) : 0u;
-            }
-            offp[j][e / 2] = o2[0] | (o2[1] << 16);
-        }
-    float* outj[kTPT];
-#pragma unroll
-    for (int j = 0; j < kTPT; ++j) outj[j] = out + (size_t)img * C * HW + rp[j];
-
-    const int nchunks = (C + kBoxC - 1) / kBoxC;
+    // ---- staged loop, instantiated per box size (compile-time plane pitch: a tap is LDS [reg + imm] + FFMA) ------------
     const int plane0 = img * C;
-    if (tid == 0) {
-        for (int s = 0; s < nst && s < nchunks; ++s) {
-            sg_mbar_expect_tx(&full_bar[s], (uint32_t)(stage_floats * 4));
-            sg_tma_load_3d(sg_smem_u32(sg_box + s * stage_floats), tmap, &full_bar[s], bx0, by0, plane0 + s * kBoxC);
-        }
-    }
-    for (int it = 0; it < nchunks; ++it) {
-        const int s = it % nst;
-        sg_mbar_wait(&full_bar[s], (uint32_t)(it / nst) & 1u);
-        const float* box = sg_box + s * stage_floats;
-        const int c0 = it * kBoxC;
-#pragma unroll
-        for (int j = 0; j < kTPT; ++j) {
-            if (!live[j] || n[j] > NE) continue;
-            float acc[kBoxC];
-#pragma unroll
-            for (int k = 0; k < kBoxC; ++k) acc[k] = 0.0f;
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                if (e < nmax) {          // warp-uniform; absent entries carry weight 0 and offset 0
-                    const float* bp = box + ((e & 1) ? (offp[j][e >> 1] >> 16) : (offp[j][e >> 1] & 0xffffu));
-#pragma unroll
-                    for (int k = 0; k < kBoxC; ++k) {
-                        float v = bp[k * plane];
-                        if (FAST) acc[k] = fmaf(v, wc[j][e], acc[k]);
-                        else { if (MODE == DRBA_SPLAT_LINEAR) v = v * wg[j][e]; acc[k] += v * wc[j][e]; }
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < kBoxC; ++k)
-                if (c0 + k < C)
-                    outj[j][(size_t)(c0 + k) * HW] = MODE == DRBA_SPLAT_SUM ? acc[k] : (FAST ? acc[k] * rden[j] : acc[k] / den[j]);
-        }
-        __syncthreads();              // every thread is done with stage s
-        if (tid == 0 && it + nst < nchunks) {
-            sg_mbar_expect_tx(&full_bar[s], (uint32_t)(stage_floats * 4));
-            sg_tma_load_3d(sg_smem_u32(sg_box + s * stage_floats), tmap, &full_bar[s], bx0, by0, plane0 + (it + nst) * kBoxC);
-        }
+    float* outb = out + (size_t)img * C * HW;
+    switch (bsel) {
+        case 0: staged_loop<MODE, 72, 20>(&maps.m[0], sg_box, full_bar, src, wc, wg, den, rden, n, live, rp, outb, nmax, bx0, by0, plane0, C, W, HW); break;
+        case 1: staged_loop<MODE, 80, 24>(&maps.m[1], sg_box, full_bar, src, wc, wg, den, rden, n, live, rp, outb, nmax, bx0, by0, plane0, C, W, HW); break;
+        default: staged_loop<MODE, 96, 32>(&maps.m[2], sg_box, full_bar, src, wc, wg, den, rden, n, live, rp, outb, nmax, bx0, by0, plane0, C, W, HW); break;
     }
 }
 
@@ -662,7 +675,7 @@ int splat_gather_launch(const float* in, const float* flow, const float* metric,
     }
     // the per-target kernel serves whatever the tile kernel left (every tile when it did not run)
     const int* done = tiled ? g.done : nullptr;
-#define GATHER(M) splat_gather_kernel<M, 8><<<grid, kGThreads, 0, st>>>(in, metric, out, g.offcnt, g.entries, N, C, H, W, eps_mode, env_dbg, done, tiles_x, tiles_y)
+#define GATHER(M) splat_gather_kernel<M, 8><<<dim3(((W + 31) / 32) * ((H + 7) / 8), N), kGThreads, 0, st>>>(in, metric, out, g.offcnt, g.entries, N, C, H, W, eps_mode, env_dbg, done, tiles_x, tiles_y)
     switch (mode) {
         case DRBA_SPLAT_SUM: GATHER(DRBA_SPLAT_SUM); break;
         case DRBA_SPLAT_AVG: GATHER(DRBA_SPLAT_AVG); break;

@@ -12,6 +12,7 @@ kernel.  Two conv engines share this schedule:
                     reference's own GPU precision under torch.autocast, models/rife.py:26)
 """
 import ctypes
+import os
 
 import torch
 
@@ -198,6 +199,7 @@ class IFNetEngine:
             for i in (1, 2):
                 self.tc[f"encode.cnn{i}"] = _tc_conv3x3(sd[f"encode.cnn{i}.weight"], sd[f"encode.cnn{i}.bias"], 1, 1, d)
             self.tc["encode.cnn3"] = _tc_convT(sd["encode.cnn3.weight"], sd["encode.cnn3.bias"], d)
+        self.flow_terms = os.environ.get("DRBA_FLOW_TERMS", "1") != "0"
         self.launches = 0   # kernels launched through this engine (bench.py reports it)
         self._sync = None   # grid-barrier words of the persistent conv programs
 
@@ -284,8 +286,17 @@ class IFNetEngine:
         return feat
 
     # ------------------------------------------------------------------ IFBlock (IFNet_HDv3.py:84-96)
-    def _assemble(self, out, out_dtype, cstride, img0, img1, f0, f1, timestep, ts_scalar, flow, prev, H, W, s):
+    def _assemble(self, out, out_dtype, cstride, img0, img1, f0, f1, timestep, ts_scalar, flow, prev, H, W, s, terms=None):
         tmp_prev, layout_prev, s_prev = prev if prev is not None else (None, 0, 1)
+        if terms:
+            # flow = sum of up-sampled lastconv outputs, evaluated at this block's sample positions (coarse blocks)
+            (t0, _, s0), (t1, _, s1) = terms[0], (terms[1] if len(terms) > 1 else (None, 0, 0))
+            with self._launch("ifnet_assemble"):
+                rc = self.L.drba_ifnet_assemble_terms(ptr(img0), ptr(img1), ptr(f0), ptr(f1), ptr(timestep), float(ts_scalar),
+                                                      ptr(t0), s0, ptr(t1), s1, ptr(tmp_prev), s_prev, ptr(out), H, W, s,
+                                                      stream_ptr(self.device))
+            self._check(rc, "drba_ifnet_assemble_terms")
+            return
         with self._launch("ifnet_assemble"):
             rc = self.L.drba_ifnet_assemble(ptr(img0), ptr(img1), ptr(f0), ptr(f1), 1 if f0.dtype == torch.float16 else 0,
                                             ptr(timestep), float(ts_scalar),
@@ -307,7 +318,8 @@ class IFNetEngine:
             nj = len(jobs)
             xs = [self._buf(("xh", bi, H, W, k), (h, w, cin_pad), f16) for k in range(nj)]
             for k, j in enumerate(jobs):
-                self._assemble(xs[k], 1, cin_pad, j["img0"], j["img1"], j["f0"], j["f1"], j["ts_t"], j["ts_s"], j["flow"], j["prev"], H, W, s)
+                self._assemble(xs[k], 1, cin_pad, j["img0"], j["img1"], j["f0"], j["f1"], j["ts_t"], j["ts_s"], j["flow"], j["prev"], H, W, s,
+                               terms=j.get("terms"))
             a = [self._buf(("ah", bi, H, W, k), (h2, w2, c // 2), f16) for k in range(nj)]
             p0 = [self._buf(("p0h", bi, H, W, k), (h4, w4, c), f16) for k in range(nj)]
             p1 = [self._buf(("p1h", bi, H, W, k), (h4, w4, c), f16) for k in range(nj)]
@@ -345,6 +357,12 @@ class IFNetEngine:
                                       self._nchw(52, h2, w2), OS=2, PY=py, PX=px)
             outs.append((ct, 0, s))
         return outs
+
+    def _flow_sum(self, tmps, flow, H, W):
+        (t0, _, s0), (t1, _, s1), (t2, _, s2) = tmps[0], tmps[1], tmps[2]
+        with self._launch("ifnet_flow_accum", nbytes=float(H * W * 16)):
+            rc = self.L.drba_ifnet_flow_sum(ptr(t0), s0, ptr(t1), s1, ptr(t2), s2, 3, ptr(flow), H, W, stream_ptr(self.device))
+        self._check(rc, "drba_ifnet_flow_sum")
 
     def _flow_accum(self, prev, flow, planar, accumulate, H, W):
         tmp, layout, s = prev
@@ -390,13 +408,26 @@ class IFNetEngine:
                 j["f0"] = self.encode(j["img0"]) if j["f0"] is None else j["f0"]
                 j["f1"] = self.encode(j["img1"]) if j["f1"] is None else j["f1"]
                 j["flow"] = self._buf(("flow", H, W, k), (H, W, 4))
+            # tensor-core engine: blocks 1 and 2 sample 1/16 and 1/4 of the pixels, so they evaluate the flow (a sum of
+            # up-sampled lastconv outputs) at their own sample positions; the full-resolution flow state is first
+            # written -- in one pass, three terms -- before block 3 (same sums, same order: IFNet_HDv3.py:157)
+            lazy = self.flow_terms and self.precision == "fp16"
             for bi in range(5):
                 if bi > 0:     # flow (+)= s * up(previous lastconv[0:4])
                     for j in jobs:
-                        self._flow_accum(j["prev"], j["flow"], None, bi > 1, H, W)
+                        if not lazy:
+                            self._flow_accum(j["prev"], j["flow"], None, bi > 1, H, W)
+                        elif bi <= 2:
+                            j["terms"] = list(j["tmps"])
+                        elif bi == 3:
+                            j["terms"] = None
+                            self._flow_sum(j["tmps"], j["flow"], H, W)
+                        else:
+                            self._flow_accum(j["prev"], j["flow"], None, True, H, W)
                 prevs = self._block(bi, jobs, H, W, self._int_scale(scale_list[bi]))
                 for j, p in zip(jobs, prevs):
                     j["prev"] = p
+                    j.setdefault("tmps", []).append(p)
             outs = []
             for j in jobs:
                 out = torch.empty((1, 3, H, W), dtype=torch.float32, device=self.device)

@@ -336,6 +336,18 @@ DRBA_API int drba_ifnet_assemble(const float* img0, const float* img1, const voi
                                  const float* timestep, float timestep_scalar,
                                  const float* flow, const float* tmp_prev, int tmp_layout, int s_prev,
                                  void* out, int out_dtype, int out_cstride, int H, int W, int s, void* stream);
+/* Tensor-core engine only (NHWC fp16 features in, [H/s][W/s][64] fp16 out, lastconv outputs NHWC fp32 pitch 16):
+ * the block input with the flow given as a SUM of up-sampled lastconv outputs, s_term0 * up(term0)[0:4]
+ * (+ s_term1 * up(term1)[0:4]), evaluated at the block's own sample positions -- the coarse blocks (scale 8, 4) read
+ * 1/16 and 1/4 of the pixels, so the full-resolution flow state need not exist for them; drba_ifnet_flow_sum then
+ * writes flow = sum of up to three terms in one pass (the state blocks 3, 4 and the blend read).  Same sums, same
+ * order as consecutive drba_ifnet_flow_accum calls (IFNet_HDv3.py:91-93, :157). */
+DRBA_API int drba_ifnet_assemble_terms(const float* img0, const float* img1, const void* f0, const void* f1,
+                                       const float* timestep, float timestep_scalar,
+                                       const float* term0, int s_term0, const float* term1, int s_term1,
+                                       const float* tmp_prev, int s_prev, void* out, int H, int W, int s, void* stream);
+DRBA_API int drba_ifnet_flow_sum(const float* tmp0, int s0, const float* tmp1, int s1, const float* tmp2, int s2, int nterms,
+                                 float* flow, int H, int W, void* stream);
 DRBA_API int drba_ifnet_flow_accum(const float* tmp, int tmp_layout, int s, float* flow, float* planar, int accumulate,
                                    int H, int W, void* stream);
 DRBA_API int drba_ifnet_blend(const float* img0, const float* img1, const float* flow, const float* tmp, int tmp_layout,

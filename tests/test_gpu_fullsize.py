@@ -288,6 +288,34 @@ def test_address_keyed_graphs_match_eager(precision):
         assert d <= 2e-3, f"output {k}: graphs vs eager differ by {d:.3g}"
 
 
+@pytest.mark.parametrize("size", [(64, 128), (1088, 1920)])
+def test_lazy_flow_terms_match_materialised_flow(size):
+    """Blocks 1 and 2 evaluate the flow as a sum of up-sampled lastconv outputs at their own sample positions and the
+    first full-resolution flow state is written in one three-term pass before block 3 (drba_ifnet_assemble_terms,
+    drba_ifnet_flow_sum) -- against the four accumulate passes of IFNet_HDv3.py:157 (engine.flow_terms = False).
+    Same sums in the same order; only FMA contraction inside the sampling kernels differs."""
+    from drba_b200.ifnet import IFNetEngine
+    torch.set_grad_enabled(False)
+    state, _ = _state()
+    h, w = size
+    g = torch.Generator(device="cpu").manual_seed(17)
+    base = F.interpolate(torch.rand((1, 3, h // 8 + 8, w // 8 + 8), generator=g), scale_factor=8, mode="bicubic").clamp(0, 1)
+    I0 = base[:, :, 0:h, 0:w].contiguous().cuda()
+    I1 = base[:, :, 3:3 + h, 5:5 + w].contiguous().cuda()
+    tmap = (0.3 + 0.4 * torch.rand((1, 1, h, w), generator=g)).cuda()
+    eng = IFNetEngine(state, "cuda", "fp16")
+    outs = []
+    for lazy in (True, False):
+        eng.flow_terms = lazy
+        outs.append([y.clone() for y in eng.forward_multi([(I0, I1, tmap, None, None), (I1, I0, 0.5, None, None)], [16, 8, 4, 2, 1])])
+    torch.cuda.synchronize()
+    for a, b in zip(*outs):
+        p = _psnr(a.cpu(), b.cpu())
+        d = float((a - b).abs().max())
+        _record(test="lazy_flow_terms", size=list(size), psnr=p, max_abs=d)
+        assert p >= 70.0 and d <= 2e-2, (p, d)
+
+
 @pytest.mark.parametrize("with_cut", [False, True])
 def test_real_rife_shards_equal_sequential(with_cut):
     """driver.interpolate_shard x 2 shards of a 12-frame clip against driver.interpolate_sequence with the REAL model

@@ -384,5 +384,5 @@ def test_softsplat_tile_path_full_size_equals_per_target_path(mode):
     metric = None if mode == "avg" else (0.5 * torch.randn((1, 1, h, w), generator=g)).cuda()
     a = softsplat(x, flow, metric, mode, _variant=3)
     b = softsplat(x, flow, metric, mode, _variant=4)
-    d = softsplat(x, flow, metric, mode)                   # the default picks the tile path
+    d = softsplat(x, flow, metric, mode)                   # the default (per-target gather)
     assert torch.equal(a, b) and torch.equal(a, d)
