@@ -75,6 +75,7 @@ SIGNATURES = {
     "drba_ifnet_assemble_terms": (_I, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _P]),
     "drba_ifnet_flow_sum": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P]),
     "drba_ifnet_blend": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P]),
+    "drba_ifnet_block_conv0a_f16": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P]),
 }
 
 
@@ -89,6 +90,12 @@ class ConvLayer(ctypes.Structure):
 
 
 CONV_MAX_LAYERS = 12
+
+
+class BlockInput(ctypes.Structure):
+    """struct drba_ifnet_block_input (include/drba_b200.h)."""
+    _fields_ = [("img0", _P), ("img1", _P), ("f0", _P), ("f1", _P), ("timestep", _P), ("timestep_scalar", _F),
+                ("flow", _P), ("tmp_prev", _P), ("s_prev", _I), ("out", _P)]
 
 
 class DrbaError(RuntimeError):

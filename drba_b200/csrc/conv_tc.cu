@@ -50,6 +50,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace drba {
 
@@ -59,6 +60,8 @@ constexpr int kStages = 6;
 constexpr int kABytesMax = 16384;      // one A stage: MT x 128 rows x Kc x 2 B
 constexpr int kStageBytes = 32768;     // streaming mode: A (<= 16 KB) | B (<= 16 KB)
 constexpr int kBRegion = 98304;        // resident mode: all weight tiles of the layer, then 6 A stages
+constexpr int kRingBytes = kStages * kStageBytes + 8192;   // whole ring; the extra 8 KB give block3.conv0a (36 KB of weights + 80 KB
+                                                           // stride-2 halo stages) a second stage: single-buffered it ran at 6600 cycles per tile
 constexpr int kMaxNTile = 128;
 constexpr int kMaxTapsTc = 9;
 constexpr int kMaxGroups = 4;
@@ -115,73 +118,6 @@ struct Program {
     LayerDev L[kMaxLayers];
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
-                                            int c0, int c1, int c2, int c3, int c4) {
-    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
-                 " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-                 " [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "setp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 16 consecutive fp32 columns of this thread's TMEM lane (no wait: pair with tc_ld_wait)
-__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 |
-// [46,48) version = 1 | [61,64) layout type (SWIZZLE_128B = 2, 64B = 4, 32B = 6)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int swz_bytes) {
-    const uint64_t layout = swz_bytes == 128 ? 2ull : (swz_bytes == 64 ? 4ull : 6ull);
-    const uint64_t sbo = (uint64_t)(8 * swz_bytes) >> 4;   // 8 rows of one swizzle span
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-
-// one lane of a converged warp, chosen by the hardware: keeps the surrounding control flow warp-uniform so
-// that TMA / MMA operands stay in uniform registers (a plain `lane == 0` branch makes the compiler
-// wrap every UTMALDG / UTCHMMA in an R2UR waterfall loop, ~150 cycles per instruction)
 // MMA issue loops, K steps unrolled.  Descriptor start addresses are (addr >> 4) in the low 14 bits: advancing
 // 16 fp16 = 32 bytes along K inside the swizzle span is +2, and shared memory (< 256 KB) never carries out of
 // the field, so offsets are plain 64-bit adds.
@@ -272,15 +208,6 @@ __device__ __noinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + er
 // conflict-free both for "lane = row" and for "four lanes per row" accesses
 constexpr int kStagingBytes = 2048;
 __device__ __forceinline__ int stg_slot(int r, int k) { return r * 4 + (k ^ ((r >> 1) & 3)); }
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "elect.sync _|p, 0xffffffff;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(pred));
-    return pred != 0;
-}
 
 // grid-wide barrier between two layers of a program: every CTA arrives once per layer
 // A CTA that never arrives (the grid was not co-resident: MPS / MIG / a foreign kernel holding SMs) would hang the
@@ -588,7 +515,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             const uint32_t group = (uint32_t)(warp - 2) >> 2;
             const int q = warp & 3;
             const int row = q * 32 + lane;
-            uint4* stg = reinterpret_cast<uint4*>(smem_raw + (smem - smem_u32(smem_raw)) + kStages * kStageBytes + (warp - 2) * kStagingBytes);
+            uint4* stg = reinterpret_cast<uint4*>(smem_raw + (smem - smem_u32(smem_raw)) + kRingBytes + (warp - 2) * kStagingBytes);
             const int row_w = pack > 1 ? 8 : tile_w;
             const int ry = row / row_w, rx = row - ry * row_w;
             const int OH = L.OH, OW = L.OW, cout = L.cout, cout_pad = L.cout_pad, act = L.act;
@@ -1093,7 +1020,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     if (L.b_sub > kStageBytes - kABytesMax) return DRBA_E_UNSUPPORTED;
     // shared-memory plan.  Resident mode: [all weight tiles of the layer | activation ring]; streaming mode: six
     // stages of [A 16 KB | B 16 KB].  Halo mode needs resident weights.
-    const long total_smem = (long)kStages * kStageBytes;
+    const long total_smem = (long)kRingBytes;
     const long w_bytes = ((long)G * L.nsplits * T * L.kchunks * L.b_sub + 1023) / 1024 * 1024;
     const long a_stage = halo_s2 ? 4 * (((long)17 * 9 * L.Kc * 2 + 1023) / 1024 * 1024) : pack > 1 ? (10 * 18 * 128 + 1023) / 1024 * 1024
                                   : (halo ? (((long)(16 * MT + 2) * 16 * L.Kc * 2 + 1023) / 1024 * 1024) : kABytesMax);
@@ -1245,7 +1172,7 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
     }
     static bool attr_set = false;
     static int max_resident = 0;
-    const size_t smem = (size_t)kBRegion + (size_t)kStages * kABytesMax + 1024 + 8 * kStagingBytes;   // ring + alignment + epilogue staging
+    const size_t smem = (size_t)kRingBytes + 1024 + 8 * kStagingBytes;   // ring + alignment + epilogue staging
     if (!attr_set) {
         cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

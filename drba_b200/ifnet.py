@@ -200,6 +200,9 @@ class IFNetEngine:
                 self.tc[f"encode.cnn{i}"] = _tc_conv3x3(sd[f"encode.cnn{i}.weight"], sd[f"encode.cnn{i}.bias"], 1, 1, d)
             self.tc["encode.cnn3"] = _tc_convT(sd["encode.cnn3.weight"], sd["encode.cnn3.bias"], d)
         self.flow_terms = os.environ.get("DRBA_FLOW_TERMS", "1") != "0"
+        # opt-in: measured SLOWER than the two separate kernels on B200 (block 4: 560 us vs 300 + 94 us; the 16 producer
+        # warps that fit next to the operand stages run at 40 % issue utilisation)
+        self.fused_conv0a = os.environ.get("DRBA_FUSED_CONV0A", "0") != "0"
         self.launches = 0   # kernels launched through this engine (bench.py reports it)
         self._sync = None   # grid-barrier words of the persistent conv programs
 
@@ -304,6 +307,21 @@ class IFNetEngine:
                                             ptr(out), out_dtype, cstride, H, W, s, stream_ptr(self.device))
         self._check(rc, "drba_ifnet_assemble")
 
+    def _block_conv0a(self, name, jobs, outs, H, W, s):
+        """Block input + conv0a in one kernel (drba_ifnet_block_conv0a_f16) for all jobs of the window."""
+        layer = self.tc[f"{name}.conv0a"]
+        arr = (_lib.BlockInput * len(jobs))()
+        for b, j, o in zip(arr, jobs, outs):
+            tmp_prev, _, s_prev = j["prev"]
+            b.img0, b.img1, b.f0, b.f1 = ptr(j["img0"]), ptr(j["img1"]), ptr(j["f0"]), ptr(j["f1"])
+            b.timestep, b.timestep_scalar = ptr(j["ts_t"]), float(j["ts_s"])
+            b.flow, b.tmp_prev, b.s_prev, b.out = ptr(j["flow"]), ptr(tmp_prev), s_prev, ptr(o)
+        oh, ow = H // s // 2, W // s // 2
+        with _lib.launch("ifnet_block_conv0a/" + name, 1, flops=len(jobs) * 2.0 * 9 * layer.cin_real * layer.cout * oh * ow):
+            rc = self.L.drba_ifnet_block_conv0a_f16(ctypes.addressof(arr), len(jobs), ptr(layer.w), ptr(layer.b), layer.cout,
+                                                    H, W, s, stream_ptr(self.device))
+        self._check(rc, "drba_ifnet_block_conv0a_f16")
+
     def _block(self, bi, jobs, H, W, s):
         """Runs block `bi` for every job (one job = one image pair: dict with img0, img1, f0, f1, ts_t, ts_s,
         flow, prev); returns per job (tmp, layout, s): the block's lastconv output (13 ch at 1/s).
@@ -316,18 +334,25 @@ class IFNetEngine:
             f16 = torch.float16
             cin_pad = 48 if bi == 0 else 64
             nj = len(jobs)
-            xs = [self._buf(("xh", bi, H, W, k), (h, w, cin_pad), f16) for k in range(nj)]
-            for k, j in enumerate(jobs):
-                self._assemble(xs[k], 1, cin_pad, j["img0"], j["img1"], j["f0"], j["f1"], j["ts_t"], j["ts_s"], j["flow"], j["prev"], H, W, s,
-                               terms=j.get("terms"))
             a = [self._buf(("ah", bi, H, W, k), (h2, w2, c // 2), f16) for k in range(nj)]
+            # blocks 3 / 4 (scale 2 / 1, materialised flow): the block input is assembled inside the kernel that runs
+            # conv0a (csrc/ifnet_fused.cu) -- the 64-channel input is never written to memory
+            fused = (self.fused_conv0a and s in (1, 2) and c // 2 in (16, 32) and h % 2 == 0 and w % 2 == 0
+                     and all(j["prev"] is not None and j["flow"] is not None and not j.get("terms") and j["prev"][1] == 1 for j in jobs))
+            if fused:
+                self._block_conv0a(name, jobs, a, H, W, s)
+            else:
+                xs = [self._buf(("xh", bi, H, W, k), (h, w, cin_pad), f16) for k in range(nj)]
+                for k, j in enumerate(jobs):
+                    self._assemble(xs[k], 1, cin_pad, j["img0"], j["img1"], j["f0"], j["f1"], j["ts_t"], j["ts_s"], j["flow"], j["prev"], H, W, s,
+                                   terms=j.get("terms"))
             p0 = [self._buf(("p0h", bi, H, W, k), (h4, w4, c), f16) for k in range(nj)]
             p1 = [self._buf(("p1h", bi, H, W, k), (h4, w4, c), f16) for k in range(nj)]
             # the last block's output is read by the blend only (flow + mask): 8 floats per pixel instead of 16
             tch = 8 if bi == len(_BLOCKS) - 1 else 16
             tmp = [self._buf(("tmp13", bi, H, W, k), (h, w, tch), torch.float32) for k in range(nj)]
-            steps = [(self.tc[f"{name}.conv0a"], h, w, xs, a, h2, w2, c // 2, None),
-                     (self.tc[f"{name}.conv0b"], h2, w2, a, p0, h4, w4, c, None)]
+            steps = [] if fused else [(self.tc[f"{name}.conv0a"], h, w, xs, a, h2, w2, c // 2, None)]
+            steps.append((self.tc[f"{name}.conv0b"], h2, w2, a, p0, h4, w4, c, None))
             cur, nxt = p0, p1
             for i in range(8):
                 steps.append((self.tc[f"{name}.res{i}"], h4, w4, cur, nxt, h4, w4, c, cur))

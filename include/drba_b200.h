@@ -346,6 +346,22 @@ DRBA_API int drba_ifnet_assemble_terms(const float* img0, const float* img1, con
                                        const float* timestep, float timestep_scalar,
                                        const float* term0, int s_term0, const float* term1, int s_term1,
                                        const float* tmp_prev, int s_prev, void* out, int H, int W, int s, void* stream);
+/* Tensor-core engine, blocks 3 and 4 (block scale s = 2 / 1): the block input is assembled INSIDE the kernel that runs the
+ * block's first conv (conv0a: 3x3, stride 2, 64 packed channels -> cout = 16 / 32, LeakyReLU 0.2; IFNet_HDv3.py:66-69), so the
+ * 64-channel input (267 MB per frame at 1088 x 1920, scale 1) is never written to memory.  Same arithmetic as
+ * drba_ifnet_assemble (DRBA_F16 output) followed by drba_conv_tc_f16; replaces both for these blocks.
+ *   jobs[k].out: [H/2s][W/2s][cout] fp16;  w: [9][cout][64] fp16 (taps ky*3+kx, packed input channel order);  bias [cout] fp32;
+ *   tmp_prev: previous block's lastconv output, NHWC fp32, 16 floats per pixel, at 1/s_prev.  Up to two jobs per launch. */
+typedef struct drba_ifnet_block_input {
+    const float* img0; const float* img1;       /* [3][H][W] fp32 */
+    const void* f0; const void* f1;             /* [H][W][16] fp16 (drba Head output) */
+    const float* timestep; float timestep_scalar; /* [H][W] fp32, or NULL -> scalar */
+    const float* flow;                          /* [H][W][4] fp32 flow state */
+    const float* tmp_prev; int s_prev;
+    void* out;
+} drba_ifnet_block_input;
+DRBA_API int drba_ifnet_block_conv0a_f16(const drba_ifnet_block_input* jobs, int njobs, const void* w, const float* bias, int cout,
+                                         int H, int W, int s, void* stream);
 DRBA_API int drba_ifnet_flow_sum(const float* tmp0, int s0, const float* tmp1, int s1, const float* tmp2, int s2, int nterms,
                                  float* flow, int H, int W, void* stream);
 DRBA_API int drba_ifnet_flow_accum(const float* tmp, int tmp_layout, int s, float* flow, float* planar, int accumulate,

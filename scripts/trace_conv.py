@@ -19,6 +19,64 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def trace_program(name, trace):
+    """blockN.program.xK: the whole IFBlock program (conv0a, conv0b, 8 ResConvs, lastconv) for K images at 1088 x 1920;
+    one line per layer: start (previous barrier out), first TMA issued, first / last traced MMA issue, last traced drain,
+    barrier in / out -- all in cycles from kernel start."""
+    from drba_b200 import _lib
+    from drba_b200.ifnet import IFNetEngine, _BLOCKS
+    from drba_b200.weights import synth_ifnet_state
+    bname, _, xk = name.split(".")
+    bi, nimg = int(bname[-1]), int(xk[1:])
+    eng16 = IFNetEngine(synth_ifnet_state(0), "cuda", "fp16")
+    H, W = 1088, 1920
+    s = [16, 8, 4, 2, 1][bi]
+    _, cin, c = _BLOCKS[bi]
+    h, w = H // s, W // s
+    h2, w2, h4, w4 = h // 2, w // 2, h // 4, w // 4
+    f16 = torch.float16
+    xs = [torch.randn((h, w, 48 if bi == 0 else 64), device="cuda").half() for _ in range(nimg)]
+    a = [torch.empty((h2, w2, c // 2), dtype=f16, device="cuda") for _ in range(nimg)]
+    p0 = [torch.empty((h4, w4, c), dtype=f16, device="cuda") for _ in range(nimg)]
+    p1 = [torch.empty((h4, w4, c), dtype=f16, device="cuda") for _ in range(nimg)]
+    tch = 8 if bi == 4 else 16
+    tmp = [torch.empty((h, w, tch), dtype=torch.float32, device="cuda") for _ in range(nimg)]
+    steps = [(eng16.tc[f"{bname}.conv0a"], h, w, xs, a, h2, w2, c // 2, None),
+             (eng16.tc[f"{bname}.conv0b"], h2, w2, a, p0, h4, w4, c, None)]
+    cur, nxt = p0, p1
+    for i in range(8):
+        steps.append((eng16.tc[f"{bname}.res{i}"], h4, w4, cur, nxt, h4, w4, c, cur))
+        cur, nxt = nxt, cur
+    steps.append((eng16.tc[f"{bname}.last"], h4, w4, cur, tmp, h4, w4, tch, None))
+    for _ in range(3):
+        eng16._conv_program(steps)
+    torch.cuda.synchronize()
+    trace.zero_()
+    _lib.lib().drba_conv_tc_debug_trace(trace.data_ptr())
+    eng16._conv_program(steps)
+    torch.cuda.synchronize()
+    _lib.lib().drba_conv_tc_debug_trace(None)
+    t = trace.cpu().tolist()
+    t0 = t[4090]
+    rel = lambda v: (v - t0) if v else None
+    print(f"== {name}: after setup+griddep {rel(t[4091])}, end {rel(t[4092])} cycles")
+    prev_out = rel(t[4091])
+    for li in range(len(steps)):
+        base = li * 256
+        tiles = [tl for tl in range(10) if t[base + tl * 16 + 1]]
+        if not tiles:
+            print(f" layer {li}: CTA 0 had no tile")
+            continue
+        last = tiles[-1]
+        drains = [rel(v) for tl in tiles for v in (t[base + tl * 16 + 9], t[base + tl * 16 + 11]) if v]
+        print(f" layer {li:2d}: start {prev_out} first_tma {rel(t[base + 1])} first_full {rel(t[base + 2])} mma_issued[0] {rel(t[base + 3])} "
+              f"mma_issued[{last}] {rel(t[base + last * 16 + 3])} last_drain {max(drains) if drains else None} "
+              f"barrier_in {rel(t[base + 202])} barrier_out {rel(t[base + 203])}"
+              f"  mma_issue_times {[rel(t[base + tl * 16 + 3]) for tl in tiles]}")
+        if t[base + 203]:
+            prev_out = rel(t[base + 203])
+
+
 def main():
     from drba_b200 import _lib
     from drba_b200.ifnet import IFNetEngine, _tc_conv3x3
@@ -29,7 +87,9 @@ def main():
              "block3.res": (64, 64, 136, 240, 1, True), "block4.res.x2": (32, 32, 544, 480, 1, True), "encode.cnn1": (16, 16, 544, 960, 1, True), "gridnet64": (64, 64, 544, 960, 1, True)}
     names = sys.argv[1:] or list(cases)
     trace = torch.zeros(4096, dtype=torch.int64, device="cuda")
-    for name in names:
+    for name in [n for n in names if ".program" in n]:
+        trace_program(name, trace)
+    for name in [n for n in names if ".program" not in n]:
         cin, cout, h, w, stride, res = cases[name]
         g = torch.Generator(device="cpu").manual_seed(1)
         wt = torch.randn((cout, cin, 3, 3), generator=g) * (1.0 / (cin * 9)) ** 0.5
