@@ -96,6 +96,8 @@ struct alignas(64) LayerDev {
     int pack;               // packed halo mode: pixels per 128-byte line (2 or 4), else 1
     int staged;             // epilogue moves residual / result through the per-warp staging tile
     int alt;                // epilogue groups take alternate tiles (whole accumulator each) instead of splitting every tile
+    int wsplit;             // resident region holds the weights of ONE N split only: tile index has the split fastest, and
+                            // every tile of a CTA belongs to split blockIdx.x % nsplits (host checks grid % nsplits == 0 or <= 1 tile per CTA)
     int ntile, nsplits, cout_pad, cout;
     int swz_bytes;          // 32 / 64 / 128
     int b_sub;              // bytes of one weight tile (padded to the swizzle period)
@@ -288,6 +290,16 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             const int ntiles_b = L.G * L.nsplits * L.T * L.kchunks;
             const int b_bytes = L.ntile * L.Kc * 2, b_sub = L.b_sub, Kc = L.Kc, kchunks = L.kchunks, T = L.T;
             const int nsplits = L.nsplits, ntile = L.ntile, cout_pad = L.cout_pad;
+            if (L.wsplit) {
+                // only this CTA's N split: tile (g, tap, kc) at index (g * T + tap) * kchunks + kc
+                const int nsplit = (int)blockIdx.x % nsplits;
+                mbar_expect_tx(&b_full, (uint32_t)(L.G * T * kchunks * b_bytes));
+                int i = 0;
+                for (int g = 0; g < L.G; ++g)
+                    for (int tap = 0; tap < T; ++tap)
+                        for (int kc = 0; kc < kchunks; ++kc, ++i)
+                            tma_load_2d(smem + (uint32_t)(i * b_sub), &L.tb, &b_full, kc * Kc, (g * T + tap) * cout_pad + nsplit * ntile);
+            } else {
             mbar_expect_tx(&b_full, (uint32_t)(ntiles_b * b_bytes));
             int i = 0;
             for (int gn = 0; gn < L.G * nsplits; ++gn) {
@@ -295,6 +307,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 for (int tap = 0; tap < T; ++tap)
                     for (int kc = 0; kc < kchunks; ++kc, ++i)
                         tma_load_2d(smem + (uint32_t)(i * b_sub), &L.tb, &b_full, kc * Kc, (g * T + tap) * cout_pad + nsplit * ntile);
+            }
             }
         }
         __syncwarp();
@@ -340,7 +353,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
         const int KI = L.KI, T = L.T, ntile = L.ntile, kchunks = L.kchunks, Kc = L.Kc, resident = L.resident;
         const uint32_t a_base = smem + (uint32_t)L.a_base;
         const uint32_t a_stride = (uint32_t)L.a_stride;
-        const int nst = L.nst, halo = L.halo, pack = L.pack;
+        const int nst = L.nst, halo = L.halo, pack = L.pack, wsplit = L.wsplit;
         const int super_h = pack > 1 ? tile_h : tile_h * MT;     // output rows of one super tile
         stage = 0;
 
@@ -354,9 +367,9 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             }
             int tl = 0;
             for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tl) {
-                const int m = idx % mtiles;
-                int r = idx / mtiles;
-                r /= nsplits;
+                int m, r;
+                if (wsplit) { r = idx / nsplits; m = r % mtiles; r /= mtiles; }
+                else { m = idx % mtiles; r = idx / mtiles; r /= nsplits; }
                 const int g = r % G, img = r / G;
                 const int ty = m / tiles_x;
                 const int oy0 = ty * super_h, ox0 = (m - ty * tiles_x) * tile_w;
@@ -450,10 +463,11 @@ conv_tc_kernel(const __grid_constant__ Program prog)
             int tl = 0;
             for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tcount, ++tl) {
                 const uint32_t buf = tcount & (uint32_t)(kAccBufs - 1), use = tcount / (uint32_t)kAccBufs;
-                int r = idx / mtiles;
-                const int nsplit = r % nsplits; r /= nsplits;
+                int r, nsplit;
+                if (wsplit) { nsplit = idx % nsplits; r = idx / nsplits / mtiles; }
+                else { r = idx / mtiles; nsplit = r % nsplits; r /= nsplits; }
                 const int g = r % G;
-                const uint32_t b_tile16 = b_res16 + (uint32_t)((g * nsplits + nsplit) * T * kchunks) * b_sub16;   // resident: tiles of (g, nsplit)
+                const uint32_t b_tile16 = b_res16 + (uint32_t)((wsplit ? g : g * nsplits + nsplit) * T * kchunks) * b_sub16;   // resident: tiles of (g, nsplit)
                 mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);     // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * (uint32_t)kMaxNTile;
@@ -537,9 +551,9 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 const uint32_t buf = tcount & (uint32_t)(kAccBufs - 1), use = tcount / (uint32_t)kAccBufs;
                 // alternate mode: this tile belongs to the other group (which signs off for both, see below)
                 if (alt && (tcount & 1u) != group) continue;
-                const int m = idx % mtiles;
-                int r = idx / mtiles;
-                const int nsplit = r % nsplits; r /= nsplits;
+                int m, r, nsplit;
+                if (wsplit) { nsplit = idx % nsplits; r = idx / nsplits; m = r % mtiles; r /= mtiles; }
+                else { m = idx % mtiles; r = idx / mtiles; nsplit = r % nsplits; r /= nsplits; }
                 const int g = r % G, img = r / G;
                 const int ty = m / tiles_x;
                 // packed halo mode: M tile mt holds the pixels x = x0 + pack * rx + mt of the same 16 rows
@@ -895,6 +909,10 @@ static CUtensorMapSwizzle swz_enum(int bytes)
     return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+static thread_local int t_ntile_cap = 1 << 30;      // build_layer retries (see the halo fall-back)
+static thread_local bool t_need_halo = false;
+static thread_local bool t_no_narrow = false;     // set while a layer is rebuilt because its split-resident form does not fit the grid
+
 static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTiledFn encode)
 {
     const int H = d.H, W = d.W, Cin = d.Cin, G = d.G, T = d.T, S = d.S, OH = d.OH, OW = d.OW;
@@ -936,9 +954,11 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
             if (S == 2) { pary = dy & 1; parx = dx & 1; cy = (dy - pary) >> 1; cx = (dx - parx) >> 1; }
             L.tapc[gi][t] = (cy + 64) | ((cx + 64) << 8) | (pary << 16) | (parx << 17);
         }
-    // N tile: <= 128 columns, a multiple of 16 that divides cout_pad
+    // N tile: <= 128 columns (<= t_ntile_cap when a retry asks for narrower tiles, see the halo fall-back below), a
+    // multiple of 16 that divides cout_pad
     int ntile = 0;
-    for (int cand = d.cout_pad < kMaxNTile ? d.cout_pad : kMaxNTile; cand >= 16; cand -= 16)
+    const int ncap = t_ntile_cap < kMaxNTile ? t_ntile_cap : kMaxNTile;
+    for (int cand = d.cout_pad < ncap ? d.cout_pad : ncap; cand >= 16; cand -= 16)
         if (d.cout_pad % cand == 0) { ntile = cand; break; }
     if (!ntile) return DRBA_E_UNSUPPORTED;
     // halo mode: a 3x3 stride-1 layer loads ONE (16*MT+2) x 16 pixel neighbourhood per K chunk and runs the nine
@@ -1021,13 +1041,38 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     // shared-memory plan.  Resident mode: [all weight tiles of the layer | activation ring]; streaming mode: six
     // stages of [A 16 KB | B 16 KB].  Halo mode needs resident weights.
     const long total_smem = (long)kRingBytes;
-    const long w_bytes = ((long)G * L.nsplits * T * L.kchunks * L.b_sub + 1023) / 1024 * 1024;
+    // (inside a narrower-N retry the resident region holds ONE N split: see wsplit)
+    const long w_bytes = ((long)G * (t_need_halo ? 1 : L.nsplits) * T * L.kchunks * L.b_sub + 1023) / 1024 * 1024;
     const long a_stage = halo_s2 ? 4 * (((long)17 * 9 * L.Kc * 2 + 1023) / 1024 * 1024) : pack > 1 ? (10 * 18 * 128 + 1023) / 1024 * 1024
                                   : (halo ? (((long)(16 * MT + 2) * 16 * L.Kc * 2 + 1023) / 1024 * 1024) : kABytesMax);
     static int env_res = -1;
     if (env_res < 0) { const char* e = getenv("DRBA_TC_RESIDENT"); env_res = e ? atoi(e) : 1; }
     bool resident = env_res && !d.bgemm && w_bytes + 2 * a_stage <= total_smem && w_bytes <= (long)kBRegion + 32768;
     if (halo && !resident) {
+        // The coarse IFNet levels (96 / 128 / 192 channels at 1/16 ... 1/64 of the frame) are bound by the bytes a CTA
+        // pulls from L2 (measured ~29 B per clock and SM whatever the box shape): with one box per tap a 128-pixel tile
+        // re-reads its input nine times (block0.res: 27 K iterations x 20 KB = 540 KB per CTA, 700 cycles each).  A
+        // NARROWER N tile whose weights fit the resident region keeps the halo mode -- the input is read once per K
+        // chunk (block0.res with 32 columns: 110 KB of weights + 3 x 36 KB) -- and spreads the layer over more SMs.
+        static int env_narrow = -1;
+        if (env_narrow < 0) { const char* e = getenv("DRBA_TC_NARROW"); env_narrow = e ? atoi(e) : 1; }
+        // Only for layers in the latency regime (<= 2 tiles per SM): large layers (GridNet's 128-channel level at 272 x 480)
+        // are better off streaming with wide N tiles (measured 55 vs 77 us).
+        if (env_narrow && !t_no_narrow && !t_need_halo && !halo_s2 && !d.bgemm && ntile > 16 && L.total_tiles <= 2 * kNumSMs) {
+            const int saved = t_ntile_cap;
+            int rc = DRBA_E_UNSUPPORTED;
+            for (int cap = ntile - 16; cap >= 16; cap -= 16) {
+                if (d.cout_pad % cap != 0) continue;
+                t_ntile_cap = cap;
+                t_need_halo = true;
+                rc = build_layer(d, nimg, L, encode);
+                t_need_halo = false;
+                if (rc == DRBA_OK) break;
+            }
+            t_ntile_cap = saved;
+            if (rc == DRBA_OK) return rc;
+        }
+        if (t_need_halo) return DRBA_E_UNSUPPORTED;      // (inside such a retry: this cap does not fit either)
         // fall back to one box per tap: redo the tile choice without the halo constraint
         halo = false;
         static thread_local int depth = 0;
@@ -1042,6 +1087,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
         }
     }
     L.resident = resident ? 1 : 0;
+    L.wsplit = (resident && t_need_halo) ? 1 : 0;
     L.halo = halo ? (halo_s2 ? 2 : 1) : 0;
     L.pack = halo ? pack : 1;
     {
@@ -1185,6 +1231,15 @@ int drba_conv_tc_program_f16(const drba_conv_layer* layers, int nlayers, int nim
     if (max_resident < 1) return DRBA_E_UNSUPPORTED;
     int grid = max_tiles < max_resident ? max_tiles : max_resident;
     if (env_grid > 0 && env_grid < grid) grid = env_grid;
+    for (int i = 0; i < nlayers; ++i) {
+        // split-resident layers need every tile of a CTA in one N split
+        if (prog.L[i].wsplit && !(prog.L[i].total_tiles <= grid || grid % prog.L[i].nsplits == 0)) {
+            t_no_narrow = true;
+            const int rc = build_layer(layers[i], nimg, prog.L[i], encode);
+            t_no_narrow = false;
+            if (rc != DRBA_OK) return rc;
+        }
+    }
     {
         // alternate-tile epilogue where a CTA walks at least four tiles of the layer (DRBA_TC_ALT: 0 never, 1 auto, 2 always)
         static int env_alt = -1;
