@@ -194,34 +194,61 @@ def measured_peaks():
     return {"hbm": 6650.0, "tensor": 1590.0, "src": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
 
 
+SPLAT_TRAFFIC_JSON = "r2_softsplat_traffic.json"
+
+
 def softsplat_roofline(dev, peaks):
-    """softsplat(C=64, soft) at 1152x1920 through drba_softsplat_f32: the flow is a smooth field with a
-    constant offset (what DRBA feeds it: flow x timestep); L2 is flushed between runs."""
+    """softsplat(C=64, soft) at 1152x1920 through drba_softsplat_f32, L2 flushed between runs, on three flows:
+    `gentle` (the headline: a smooth field with a constant offset, what DRBA feeds it: flow x timestep), `smooth8`
+    (the same field at 4x the amplitude: stronger divergence / folds) and `random` (independent N(0, 8 px) per pixel:
+    SURVEY.md 8d's worst case).  achieved = algorithmic bytes (input + flow + metric read once, output written once)
+    / time of the whole call (list build + gather); traffic = ncu dram bytes of the same call (profiles/)."""
     from drba_b200.softsplat import softsplat
     c, h, w = 64, 1152, 1920
-    g = torch.Generator(device="cpu").manual_seed(1)
-    lo = 2.0 * torch.randn((1, 2, h // 16, w // 16), generator=g)
-    flow = (torch.nn.functional.interpolate(lo, size=(h, w), mode="bilinear", align_corners=False) + 6.5).to(dev)
     x = torch.randn((1, c, h, w), device=dev)
     metric = torch.randn((1, 1, h, w), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for _ in range(3):
-        softsplat(x, flow, metric, "soft")
-    ts = []
-    for _ in range(7):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        softsplat(x, flow, metric, "soft")
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    ms = sorted(ts)[len(ts) // 2]
     nbytes = h * w * 4 * ((c + 3) + c)
+
+    def smooth(amp):
+        g = torch.Generator(device="cpu").manual_seed(1)
+        lo = amp * torch.randn((1, 2, h // 16, w // 16), generator=g)
+        return torch.nn.functional.interpolate(lo, size=(h, w), mode="bilinear", align_corners=False)
+
+    def run(flow, reps):
+        for _ in range(2):
+            softsplat(x, flow, metric, "soft")
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            softsplat(x, flow, metric, "soft")
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2]
+
+    g2 = torch.Generator(device="cpu").manual_seed(2)
+    flows = {"gentle": (smooth(2.0) + 6.5).to(dev), "smooth8": smooth(8.0).to(dev),
+             "random": (8.0 * torch.randn((1, 2, h, w), generator=g2)).to(dev)}
+    per_flow = {}
+    for name, flow in flows.items():
+        ms = run(flow, 7 if name == "gentle" else 3)
+        per_flow[name] = {"ms": round(ms, 4), "GBps": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / peaks["hbm"], 4)}
+    traffic, tsrc = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", SPLAT_TRAFFIC_JSON)) as f:
+            tj = json.load(f)
+        traffic, tsrc = tj["dram_bytes_per_call"], f"profiles/{SPLAT_TRAFFIC_JSON} ({tj['source']})"
+    except Exception:
+        pass
+    ms = per_flow["gentle"]["ms"]
     ach = nbytes / ms / 1e6
     return {"kernel": "softsplat (count/scan/fill/gather, csrc/splat_gather.cu)", "bound": "hbm", "achieved": round(ach, 1),
             "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4), "ms": round(ms, 4),
-            "workload": "C=64 soft 1152x1920 fp32 NCHW, smooth flow; 6 launches per call", "traffic": None}
+            "workload": "C=64 soft 1152x1920 fp32 NCHW, gentle flow (headline); 6 launches per call", "flows": per_flow,
+            "algorithmic_bytes": nbytes, "traffic": traffic, "traffic_source": tsrc}
 
 
 # ------------------------------------------------------------------------------------------

@@ -71,7 +71,7 @@ def run_program(steps, device, tag=""):
             c.epilogue, c.act, c.out_cstride, c.out_os = layer.epilogue, s.act, s.cstride, layer.out_os
             c.act1, c.act2, c.slope0, c.slope1, c.slope2 = s.act1, s.act2, s.slope0, s.slope1, s.slope2
             c.bgemm = s.bgemm
-            flops += nimg * 2.0 * layer.G * layer.T * layer.cin_real * layer.cout * s.OH * s.OW
+            flops += nimg * 2.0 * getattr(layer, "flop_taps", layer.G * layer.T) * layer.cin_real * layer.cout * s.OH * s.OW
         with _lib.launch("conv_tc_f16" + (("/" + tag) if tag else ""), 1, flops=flops):
             rc = L.drba_conv_tc_program_f16(ctypes.addressof(arr), len(chunk), nimg, ptr(_sync(device)), stream_ptr(device))
         _lib.check(rc, "drba_conv_tc_program_f16")

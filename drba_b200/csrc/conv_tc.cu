@@ -39,9 +39,14 @@
 //    (the epilogue of tile i overlaps the main loop of tile i+1).  The plain epilogue exists in two
 //    template variants: one lane per pixel row, or rows moved four lanes per pixel through a
 //    swizzled per-warp staging tile (coalesced residual / result traffic for wide rows);
-//  * a tcgen05.mma with M = 128 costs ~115-121 cycles for N = 32 / 64 (an operand arrives at about one
-//    32-byte row segment per cycle), so at IFNet's channel counts the MMA count, not the FLOP count,
-//    sets the main-loop time: the ceiling of this GEMM view is N/256 of the tensor peak;
+//  * measured in isolation (scripts/mma_shapes.cu, profiles/r2_mma_shapes.json) a tcgen05.mma with M = 128, K = 16 costs
+//    max((32 M + 32 N) / 128, M N / 256) cycles: 40 / 48 / 64 for N = 32 / 64 / 128 -- the operand bytes over 128 B/clk
+//    of shared-memory read bandwidth, or the math floor.  What bounds the layers in practice is elsewhere: an SM pulls
+//    ~29 B per clock from L2 whatever the box shape (block4.conv0a: 78 KB per tile in 2700 cycles; block0.res: 20 KB
+//    per K iteration in 700), and every layer boundary (drain, fence, grid barrier, refill) costs ~15k cycles;
+//  * layers in the latency regime whose weights do not fit the resident region take a narrower N tile and keep ONE
+//    N split resident per CTA (tile index with the split fastest, LayerDev::wsplit): they stay in halo mode and read
+//    their input once per K chunk instead of once per tap (block0.res: 540 KB -> 218 KB per CTA, 12.4 -> 6.9 us);
 //  * consecutive layers (a whole IFBlock: conv0a, conv0b, 8 x ResConv, lastconv) are chained inside
 //    the launch with a grid-wide barrier (release/acquire counter in global memory) instead of a
 //    kernel boundary; up to two independent images (the two interpolated frames of a DRBA window)
@@ -815,7 +820,8 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                     } else {
                         // lastconv: group g = phase (py, px); channel co = c13*4 + i*2 + j lands at
                         // out[4*oy + 2*py + i][4*ox + 2*px + j][c13]  (ConvTranspose phase + PixelShuffle(2))
-                        const int py = g >> 1, px = g & 1;
+                        const int ph = G == 1 ? nsplit : g;       // 3x3 form: the N split is the phase
+                        const int py = ph >> 1, px = ph & 1;
                         const int OW4 = OW * 4;
                         float* out = reinterpret_cast<float*>(L.out[img]);
                         // out_cstride = floats per pixel: 16, or 8 when only the channels 0..7 are wanted (the last IFBlock's
@@ -924,7 +930,11 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     if (S == 2 && (H % 2 != 0 || W % 2 != 0)) return DRBA_E_ARG;
     if (d.cout_pad <= 0 || d.cout_pad % 16 != 0 || d.cout <= 0 || d.cout > d.cout_pad) return DRBA_E_ARG;
     if (d.epilogue != 0 && d.epilogue != 1) return DRBA_E_ARG;
-    if (d.epilogue == 1 && (d.cout_pad != 64 || d.cout != 52 || G != 4 || (d.out_cstride != 16 && d.out_cstride != 8))) return DRBA_E_ARG;
+    // lastconv: four phase convs of four taps (G = 4, 64 padded channels each), or -- same arithmetic, zero weights on
+    // the five taps a phase does not use -- ONE 3x3 conv with 4 x 64 output columns whose N split IS the phase
+    const bool last3x3 = d.epilogue == 1 && G == 1 && T == 9 && d.cout_pad == 256 && S == 1;
+    if (d.epilogue == 1 && !last3x3 && (d.cout_pad != 64 || d.cout != 52 || G != 4)) return DRBA_E_ARG;
+    if (d.epilogue == 1 && (d.cout != 52 || (d.out_cstride != 16 && d.out_cstride != 8))) return DRBA_E_ARG;
     if (d.out_os != 1 && d.out_os != 2) return DRBA_E_ARG;
     if (d.epilogue == 0 && ((d.out_os == 1 && G != 1) || (d.out_os == 2 && G != 4))) return DRBA_E_ARG;
     if (d.epilogue == 0 && (d.out_cstride < d.cout_pad || d.out_cstride % 8 != 0)) return DRBA_E_ARG;
@@ -961,6 +971,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     for (int cand = d.cout_pad < ncap ? d.cout_pad : ncap; cand >= 16; cand -= 16)
         if (d.cout_pad % cand == 0) { ntile = cand; break; }
     if (!ntile) return DRBA_E_UNSUPPORTED;
+    if (last3x3) ntile = 64;          // one phase per N split (the pixel-shuffle epilogue reads 64 columns)
     // halo mode: a 3x3 stride-1 layer loads ONE (16*MT+2) x 16 pixel neighbourhood per K chunk and runs the nine
     // taps as descriptor offsets into it (8-pixel-wide tiles keep every 8-row core group contiguous; the 16-pixel
     // pitch keeps the swizzle phase identical for all groups) -- 4x fewer activation bytes than one box per tap.
@@ -971,7 +982,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
         e = getenv("DRBA_TC_PACK"); env_pack = e ? atoi(e) : 1;
         e = getenv("DRBA_TC_HALO_S2"); env_s2 = e ? atoi(e) : 1;
     }
-    bool halo = env_halo && (S == 1 || (S == 2 && env_s2)) && T == 9 && G == 1 && d.epilogue == 0 && !d.bgemm;
+    bool halo = env_halo && (S == 1 || (S == 2 && env_s2)) && T == 9 && G == 1 && (d.epilogue == 0 || last3x3) && !d.bgemm;
     if (halo)
         for (int t = 0; t < 9; ++t)
             if (d.dy[t] != t / 3 - 1 || d.dx[t] != t % 3 - 1) halo = false;
@@ -1058,10 +1069,11 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
         if (env_narrow < 0) { const char* e = getenv("DRBA_TC_NARROW"); env_narrow = e ? atoi(e) : 1; }
         // Only for layers in the latency regime (<= 2 tiles per SM): large layers (GridNet's 128-channel level at 272 x 480)
         // are better off streaming with wide N tiles (measured 55 vs 77 us).
-        if (env_narrow && !t_no_narrow && !t_need_halo && !halo_s2 && !d.bgemm && ntile > 16 && L.total_tiles <= 2 * kNumSMs) {
+        if (env_narrow && !t_no_narrow && !t_need_halo && !halo_s2 && !d.bgemm && ntile >= 16 && (last3x3 || L.total_tiles <= 2 * kNumSMs)) {
             const int saved = t_ntile_cap;
             int rc = DRBA_E_UNSUPPORTED;
-            for (int cap = ntile - 16; cap >= 16; cap -= 16) {
+            // (first the same width with one split resident, then narrower ones; the 3x3 lastconv keeps its 64 columns)
+            for (int cap = ntile; cap >= (last3x3 ? ntile : 16); cap -= 16) {
                 if (d.cout_pad % cap != 0) continue;
                 t_ntile_cap = cap;
                 t_need_halo = true;

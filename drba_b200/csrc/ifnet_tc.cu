@@ -61,12 +61,28 @@ __global__ void __launch_bounds__(kIfThreads)
 ifnet_assemble_v2_kernel(const AssembleParams p)
 {
     __shared__ __align__(16) uint4 tile[kAsmTile * 8];
+    // Flow given as a SUM of up-sampled lastconv outputs (coarse blocks, NP = 4): evaluated ONCE per sample position
+    // -- 32 pixels x 4 positions = one per thread -- and shared; each of the four roles used to re-evaluate it (two
+    // bilinear up-samplings = 24 loads per position: block2's kernel took 57 us for 130 k output pixels).
+    __shared__ __align__(16) float4 sflow[NP == 4 ? kAsmTile * 4 : 1];
     const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hw = p.h * p.w;
     const int base = blockIdx.x * kAsmTile;
     const int off = NP == 1 ? 0 : p.s / 2 - 1;
     const size_t HW = (size_t)p.H * p.W;
     constexpr int PXW = NP == 1 ? 16 : 8;      // output pixels per warp pass
+    const bool shared_flow = NP == 4 && p.nfterms > 0;
+    if (shared_flow) {
+        const int px = threadIdx.x >> 2, K = threadIdx.x & 3;
+        const int idx = min(base + px, hw - 1);
+        const int Y = idx / p.w, X = idx - Y * p.w;
+        sflow[threadIdx.x] = load_flow<1>(p, p.s * Y + off + (K >> 1), p.s * X + off + (K & 1));
+        __syncthreads();
+    }
+    // flow at sample position K = 2 * (row offset) + (column offset) of tile pixel px
+    auto flow_at = [&](int px, int K, int y, int x) -> float4 {
+        return shared_flow ? sflow[px * 4 + K] : load_flow<1>(p, y, x);
+    };
 
     if (role < 2) {
         // lane = [pixel | x position | channel half]
@@ -81,13 +97,13 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
             const int x = p.s * X + off + xpos, y = p.s * Y + off;
             float r0[8];
             {
-                const float4 fl = load_flow<1>(p, y, x);
+                const float4 fl = flow_at(px, xpos, y, x);
                 const WarpTap t = warp_tap(x, y, role == 0 ? fl.x : fl.z, role == 0 ? fl.y : fl.w, p.H, p.W);
                 sample_feat8(f, t, r0);
             }
             if (NP == 4) {
                 float r1[8];
-                const float4 fl = load_flow<1>(p, y + 1, x);
+                const float4 fl = flow_at(px, 2 + xpos, y + 1, x);
                 const WarpTap t = warp_tap(x, y + 1, role == 0 ? fl.x : fl.z, role == 0 ? fl.y : fl.w, p.H, p.W);
                 sample_feat8(f, t, r1);
 #pragma unroll
@@ -113,14 +129,14 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
             const int x = p.s * X + off + xpos, y = p.s * Y + off;
             float r0[3];
             {
-                const float4 fl = load_flow<1>(p, y, x);
+                const float4 fl = flow_at(px, xpos, y, x);
                 const WarpTap t = warp_tap(x, y, sel ? fl.z : fl.x, sel ? fl.w : fl.y, p.H, p.W);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) r0[c] = sample_plane(img + (size_t)c * HW, t);
             }
             if (NP == 4) {
                 float r1[3];
-                const float4 fl = load_flow<1>(p, y + 1, x);
+                const float4 fl = flow_at(px, 2 + xpos, y + 1, x);
                 const WarpTap t = warp_tap(x, y + 1, sel ? fl.z : fl.x, sel ? fl.w : fl.y, p.H, p.W);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) r1[c] = sample_plane(img + (size_t)c * HW, t);
@@ -153,7 +169,7 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
             const int Y = idx / p.w, X = idx - Y * p.w;
             const int x = p.s * X + off + (K & 1), y = p.s * Y + off + (K >> 1);
             float v[16];
-            const float4 fl = load_flow<1>(p, y, x);
+            const float4 fl = flow_at(px, K, y, x);
             v[0] = p.timestep ? p.timestep[(size_t)y * p.W + x] : p.timestep_scalar;
             up_tmp<1, 4, 9>(p.prev, y, x, v + 1);
             v[10] = fl.x; v[11] = fl.y; v[12] = fl.z; v[13] = fl.w;

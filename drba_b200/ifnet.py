@@ -135,6 +135,26 @@ def _tc_lastconv(weight, bias, device):
     return _TcLayer(wp, bp, dys, dxs, 1, 0, cout, 1, device)
 
 
+def _tc_lastconv3x3(weight, bias, device):
+    """The same lastconv as ONE 3x3 conv with 4 x 64 output columns (phase-major): a phase's weights are zero on the
+    five taps it does not use.  2.25x the MMAs, but the layer can then run in the conv engine's halo mode with one
+    phase's weights resident per CTA: its input is read once per tile instead of once per (phase, tap)."""
+    cin, cout = weight.shape[0], weight.shape[1]       # [Cin, 52, 4, 4]
+    wp = torch.zeros((1, 9, 256, cin))
+    bp = torch.zeros((1, 256))
+    for py in (0, 1):
+        for px in (0, 1):
+            g = py * 2 + px
+            for ky, ddy in _CT_PHASE[py]:
+                for kx, ddx in _CT_PHASE[px]:
+                    wp[0, (ddy + 1) * 3 + (ddx + 1), g * 64:g * 64 + cout, :] = weight[:, :, ky, kx].float().t()
+            bp[0, g * 64:g * 64 + cout] = bias.float()
+    dy, dx = _taps3x3()
+    layer = _TcLayer(wp, bp, dy, dx, 1, 0, cout, 1, device)
+    layer.flop_taps = 16        # algorithmic FLOPs: four phases x four taps, not the nine zero-padded taps x one group issued
+    return layer
+
+
 def _tc_convT(weight, bias, device):
     """ConvTranspose2d(cin, cout, 4, 2, 1) as four phase convs writing NHWC fp16 at (2y+py, 2x+px)."""
     cin, cout = weight.shape[0], weight.shape[1]
@@ -195,7 +215,9 @@ class IFNetEngine:
                 for i in range(8):
                     p = f"{name}.convblock.{i}"
                     self.tc[f"{name}.res{i}"] = _tc_conv3x3(sd[p + ".conv.weight"], sd[p + ".conv.bias"], 1, 1, d, sd[p + ".beta"])
-                self.tc[f"{name}.last"] = _tc_lastconv(sd[f"{name}.lastconv.0.weight"], sd[f"{name}.lastconv.0.bias"], d)
+                # blocks 3 / 4 (64 / 32 channels: one phase's 3x3 weights fit shared memory): the 3x3 form
+                last3 = c <= 64 and os.environ.get("DRBA_LAST3X3", "1") != "0"
+                self.tc[f"{name}.last"] = (_tc_lastconv3x3 if last3 else _tc_lastconv)(sd[f"{name}.lastconv.0.weight"], sd[f"{name}.lastconv.0.bias"], d)
             for i in (1, 2):
                 self.tc[f"encode.cnn{i}"] = _tc_conv3x3(sd[f"encode.cnn{i}.weight"], sd[f"encode.cnn{i}.bias"], 1, 1, d)
             self.tc["encode.cnn3"] = _tc_convT(sd["encode.cnn3.weight"], sd["encode.cnn3.bias"], d)
@@ -234,7 +256,7 @@ class IFNetEngine:
 
     def _conv_tc(self, layer, x, H, W, out, OH, OW, out_cstride, res=None, tag=""):
         # algorithmic FLOPs: real channels only (2 * Cin * Cout * taps * Hout * Wout)
-        with self._launch("conv_tc_f16" + (("/" + tag) if tag else ""), flops=2.0 * layer.G * layer.T * layer.cin_real * layer.cout * OH * OW):
+        with self._launch("conv_tc_f16" + (("/" + tag) if tag else ""), flops=2.0 * getattr(layer, "flop_taps", layer.G * layer.T) * layer.cin_real * layer.cout * OH * OW):
             rc = self.L.drba_conv_tc_f16(ptr(x), H, W, layer.cin, ptr(layer.w), ptr(layer.b), layer.G, layer.T,
                                          layer.dy, layer.dx, layer.cout_pad, layer.cout, layer.stride, OH, OW,
                                          layer.epilogue, layer.act, ptr(res), ptr(out), out_cstride, layer.out_os, stream_ptr(self.device))

@@ -196,7 +196,9 @@ DRBA_API int drba_conv2d_direct_f32(const float* in, const float* w, const float
  *                         [2*OH][2*OW][out_cstride], phase g lands at (2*oy + py, 2*ox + px)  (Head.cnn3)
  *   epilogue 1: lastconv = ConvTranspose2d(Cin,52,4,2,1)+PixelShuffle(2): G = 4 phases (py*2+px),
  *               T = 4, cout_pad = 64, cout = 52; out = NHWC fp32 [4*OH][4*OW][out_cstride], out_cstride = 16
- *               (13 used) or 8 (channels 0..7 only: flow, mask, feat 0..2)
+ *               (13 used) or 8 (channels 0..7 only: flow, mask, feat 0..2).  Equivalent 3x3 form: G = 1, T = 9 (canonical
+ *               taps), cout_pad = 256 = 4 phases x 64 with zero weights on the taps a phase does not use (halo mode, one
+ *               phase's weights resident per CTA)
  * ------------------------------------------------------------------------- */
 DRBA_API int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
                               const void* w, const float* bias, int G, int T, const int* dy, const int* dx,

@@ -97,7 +97,7 @@ def main():
                 steps.append((eng16.tc[f"{name}.res{i}"], h4, w4, cur, nxt, h4, w4, c, cur))
                 cur, nxt = nxt, cur
             steps.append((eng16.tc[f"{name}.last"], h4, w4, cur, tmp, h4, w4, 16, None))
-            flops = sum(nimg * 2.0 * l.G * l.T * l.cin_real * l.cout * oh * ow for (l, _, _, _, _, oh, ow, _, _) in steps)
+            flops = sum(nimg * 2.0 * getattr(l, "flop_taps", l.G * l.T) * l.cin_real * l.cout * oh * ow for (l, _, _, _, _, oh, ow, _, _) in steps)
             s_ = torch.cuda.Stream()
             with torch.cuda.stream(s_):
                 eng16._conv_program(steps)
