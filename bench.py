@@ -820,7 +820,7 @@ def main():
         dist.destroy_process_group()
 
 
-TRAFFIC_JSON = "r1_conv_tc_traffic.json"
+TRAFFIC_JSON = "r2_conv_tc_traffic.json"
 
 
 def _emit(line):

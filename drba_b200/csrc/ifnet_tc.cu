@@ -66,16 +66,16 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
     // bilinear up-samplings = 24 loads per position: block2's kernel took 57 us for 130 k output pixels).
     __shared__ __align__(16) float4 sflow[NP == 4 ? kAsmTile * 4 : 1];
     const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hw = p.h * p.w;
-    const int base = blockIdx.x * kAsmTile;
+    // grid = (ceil(w / 32), h): a CTA owns 32 x-adjacent pixels of ONE output row, so no pass divides by the row length
+    // (a signed division is ~25 instructions, seven passes per CTA, and the kernel is issue-bound)
+    const int Y = blockIdx.y, X0 = blockIdx.x * kAsmTile;
     const int off = NP == 1 ? 0 : p.s / 2 - 1;
     const size_t HW = (size_t)p.H * p.W;
     constexpr int PXW = NP == 1 ? 16 : 8;      // output pixels per warp pass
     const bool shared_flow = NP == 4 && p.nfterms > 0;
     if (shared_flow) {
         const int px = threadIdx.x >> 2, K = threadIdx.x & 3;
-        const int idx = min(base + px, hw - 1);
-        const int Y = idx / p.w, X = idx - Y * p.w;
+        const int X = min(X0 + px, p.w - 1);
         sflow[threadIdx.x] = load_flow<1>(p, p.s * Y + off + (K >> 1), p.s * X + off + (K & 1));
         __syncthreads();
     }
@@ -92,8 +92,7 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
 #pragma unroll 1
         for (int pass = 0; pass < kAsmTile / PXW; ++pass) {
             const int px = pass * PXW + pl;
-            const int idx = min(base + px, hw - 1);
-            const int Y = idx / p.w, X = idx - Y * p.w;
+            const int X = min(X0 + px, p.w - 1);
             const int x = p.s * X + off + xpos, y = p.s * Y + off;
             float r0[8];
             {
@@ -124,8 +123,7 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
 #pragma unroll 1
         for (int pass = 0; pass < kAsmTile / PXW; ++pass) {
             const int px = pass * PXW + pl;
-            const int idx = min(base + px, hw - 1);
-            const int Y = idx / p.w, X = idx - Y * p.w;
+            const int X = min(X0 + px, p.w - 1);
             const int x = p.s * X + off + xpos, y = p.s * Y + off;
             float r0[3];
             {
@@ -165,8 +163,7 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
 #pragma unroll 1
         for (int pass = 0; pass < kAsmTile / PXM; ++pass) {
             const int px = pass * PXM + pl;
-            const int idx = min(base + px, hw - 1);
-            const int Y = idx / p.w, X = idx - Y * p.w;
+            const int X = min(X0 + px, p.w - 1);
             const int x = p.s * X + off + (K & 1), y = p.s * Y + off + (K >> 1);
             float v[16];
             const float4 fl = flow_at(px, K, y, x);
@@ -190,18 +187,18 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
         }
     }
     __syncthreads();
-    uint4* out4 = reinterpret_cast<uint4*>(p.out);
+    uint4* out4 = reinterpret_cast<uint4*>(p.out) + ((size_t)Y * p.w + X0) * 8;
 #pragma unroll
     for (int k = 0; k < kAsmTile * 8 / kIfThreads; ++k) {
         const int i = threadIdx.x + k * kIfThreads;
         const int px = i >> 3, c = i & 7;
-        if (base + px < hw) out4[(size_t)(base + px) * 8 + c] = tile[tile_slot(px, c)];
+        if (X0 + px < p.w) out4[(size_t)px * 8 + c] = tile[tile_slot(px, c)];
     }
 }
 
 void launch_assemble_tc(const AssembleParams& p, cudaStream_t st)
 {
-    const unsigned grid = cdiv((size_t)p.h * p.w, kAsmTile);
+    const dim3 grid(cdiv((size_t)p.w, kAsmTile), (unsigned)p.h);
     if (p.s == 1) ifnet_assemble_v2_kernel<1><<<grid, kIfThreads, 0, st>>>(p);
     else ifnet_assemble_v2_kernel<4><<<grid, kIfThreads, 0, st>>>(p);
 }
