@@ -68,7 +68,7 @@ constexpr int kBRegion = 98304;        // resident mode: all weight tiles of the
 constexpr int kRingBytes = kStages * kStageBytes + 8192;   // whole ring; the extra 8 KB give block3.conv0a (36 KB of weights + 80 KB
                                                            // stride-2 halo stages) a second stage: single-buffered it ran at 6600 cycles per tile
 constexpr int kMaxNTile = 128;
-constexpr int kMaxTapsTc = 9;
+constexpr int kMaxTapsTc = 10;          // 3x3 + the identity tap of a ResConv (residual added by the tensor core)
 constexpr int kMaxGroups = 4;
 constexpr int kAccBufs = 4;            // accumulator ring in tensor memory
 constexpr int kTmemCols = kAccBufs * kMaxNTile;   // four accumulators of <= 128 columns = all 512 columns (one CTA per SM)
@@ -142,16 +142,20 @@ __device__ __forceinline__ void issue_tile(uint32_t tmem_d, uint64_t da0, uint64
 
 // halo mode (canonical 3x3 taps, checked on the host): tap (ty, tx) of M tile mt starts at halo pixel
 // ((mt * 16 + ty) * 16 + tx); the tap's weight tile is b_tap16 further on
+// (tap 9, present when ntaps == 10, is the IDENTITY tap of a ResConv: the centre pixel against a unit weight tile, so the
+// residual is accumulated exactly in fp32 by the tensor core and the epilogue has no residual to fetch)
 template <int KS>
 __device__ __forceinline__ void issue_halo(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t rowb16, uint32_t b_tap16,
-                                           int MT, int ntile, uint32_t idesc, uint32_t accumulate)
+                                           int MT, int ntile, uint32_t idesc, uint32_t accumulate, int ntaps)
 {
     for (int mt = 0; mt < MT; ++mt) {
         const uint64_t da_mt = da0 + (uint64_t)((uint32_t)(mt * 256) * rowb16);
         const uint32_t d = tmem_d + mt * ntile;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t da = da_mt + (uint64_t)((uint32_t)((tap / 3) * 16 + tap % 3) * rowb16);
+        for (int tap = 0; tap < 10; ++tap) {
+            if (tap == 9 && ntaps < 10) break;
+            const int ty = tap == 9 ? 1 : tap / 3, tx = tap == 9 ? 1 : tap % 3;
+            const uint64_t da = da_mt + (uint64_t)((uint32_t)(ty * 16 + tx) * rowb16);
             const uint64_t db = db0 + (uint64_t)((uint32_t)tap * b_tap16);
 #pragma unroll
             for (int k = 0; k < KS; ++k)
@@ -189,7 +193,7 @@ __device__ __forceinline__ void issue_halo_s2(uint32_t tmem_d, uint64_t da0, uin
 // advance.  Eight consecutive lines are one core group; the next image row is 10 lines further (SBO = 1280 B).
 template <int P>
 __device__ __forceinline__ void issue_halo_packed(uint32_t tmem_d, uint64_t da0, uint64_t db0, uint32_t b_tap16, int ntile,
-                                                  uint32_t idesc, uint32_t accumulate)
+                                                  uint32_t idesc, uint32_t accumulate, int ntaps)
 {
     constexpr int KS = 4 / P;            // Kc = 64 / P channels = KS steps of 16
     constexpr int SUB16 = 8 / P;         // one pixel inside the line, in 16-byte units
@@ -197,9 +201,11 @@ __device__ __forceinline__ void issue_halo_packed(uint32_t tmem_d, uint64_t da0,
     for (int p = 0; p < P; ++p) {
         const uint32_t d = tmem_d + p * ntile;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int q = p + tap % 3 - 1 + P;
-            const uint64_t da = da0 + (uint64_t)(((tap / 3) * 10 + q / P) * 8 + (q % P) * SUB16);
+        for (int tap = 0; tap < 10; ++tap) {
+            if (tap == 9 && ntaps < 10) break;
+            const int ty = tap == 9 ? 1 : tap / 3, tx = tap == 9 ? 1 : tap % 3;
+            const int q = p + tx - 1 + P;
+            const uint64_t da = da0 + (uint64_t)((ty * 10 + q / P) * 8 + (q % P) * SUB16);
             const uint64_t db = db0 + (uint64_t)((uint32_t)tap * b_tap16);
 #pragma unroll
             for (int k = 0; k < KS; ++k)
@@ -487,8 +493,8 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                             const uint64_t da0 = desc_a_packed | (uint64_t)sa16;
                             const uint64_t db0 = desc_hi | (uint64_t)b_tile16;
                             if (ksteps == 0) {}
-                            else if (pack == 2) issue_halo_packed<2>(tmem_d, da0, db0, b_tap16, ntile, idesc, accumulate);
-                            else issue_halo_packed<4>(tmem_d, da0, db0, b_tap16, ntile, idesc, accumulate);
+                            else if (pack == 2) issue_halo_packed<2>(tmem_d, da0, db0, b_tap16, ntile, idesc, accumulate, T);
+                            else issue_halo_packed<4>(tmem_d, da0, db0, b_tap16, ntile, idesc, accumulate, T);
                         } else if (halo == 2) {
                             const uint64_t da0 = desc_hi_s2 | (uint64_t)sa16;
                             const uint64_t db0 = desc_hi | (uint64_t)(b_tile16 + (uint32_t)it * b_sub16);
@@ -502,9 +508,9 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                             const uint64_t da0 = desc_hi_halo | (uint64_t)sa16;
                             const uint64_t db0 = desc_hi | (uint64_t)(b_tile16 + (uint32_t)it * b_sub16);
                             switch (ksteps) {
-                                case 1: issue_halo<1>(tmem_d, da0, db0, rowb16, b_tap16, MT, ntile, idesc, accumulate); break;
-                                case 2: issue_halo<2>(tmem_d, da0, db0, rowb16, b_tap16, MT, ntile, idesc, accumulate); break;
-                                case 4: issue_halo<4>(tmem_d, da0, db0, rowb16, b_tap16, MT, ntile, idesc, accumulate); break;
+                                case 1: issue_halo<1>(tmem_d, da0, db0, rowb16, b_tap16, MT, ntile, idesc, accumulate, T); break;
+                                case 2: issue_halo<2>(tmem_d, da0, db0, rowb16, b_tap16, MT, ntile, idesc, accumulate, T); break;
+                                case 4: issue_halo<4>(tmem_d, da0, db0, rowb16, b_tap16, MT, ntile, idesc, accumulate, T); break;
                                 default: break;
                             }
                         } else {
@@ -832,6 +838,37 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                             tc_ld16_nowait(taddr + c0, rr);
                             tc_ld16_nowait(taddr + c0 + 16, rr + 16);
                             tc_ld_wait();
+                            if (L.staged) {
+                                // Through the per-warp staging tile: a lane's four 16-byte pieces of one output row (two
+                                // sub-pixels x two channel quads) are 64 contiguous bytes (32 + 32 with 16 floats per pixel);
+                                // written lane-per-row they scatter into 32 lines per STG.128 (the layer was bound by LSU
+                                // wavefronts: 4600 cycles per 256-pixel tile), written four lanes per row into 8.
+                                float vv[2][16];
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) vv[hh][i] = __uint_as_float(rr[hh * 16 + i]) + bias[c0 + hh * 16 + i];
+                                const int kq = lane & 3, sb = lane >> 2;
+                                const int doff = (kq >> 1) * cstride + ((c0 + (kq & 1) * 16) >> 2);
+#pragma unroll
+                                for (int i2 = 0; i2 < 2; ++i2) {
+                                    const int myoff = valid ? (int)(((size_t)(4 * oy + 2 * py + i2) * OW4 + 4 * ox + 2 * px) * cstride) : -1;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const int ij = i2 * 2 + (k >> 1), hh = k & 1;
+                                        const float4 o = make_float4(vv[hh][0 + ij], vv[hh][4 + ij], vv[hh][8 + ij], vv[hh][12 + ij]);
+                                        reinterpret_cast<float4*>(stg)[stg_slot(lane, k)] = o;
+                                    }
+                                    __syncwarp();
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) {
+                                        const int o = __shfl_sync(0xffffffffu, myoff, sb + 8 * t);
+                                        if (o >= 0) *reinterpret_cast<float4*>(out + o + doff) = reinterpret_cast<const float4*>(stg)[stg_slot(sb + 8 * t, kq)];
+                                    }
+                                    __syncwarp();
+                                }
+                                continue;
+                            }
                             if (!valid) continue;
 #pragma unroll
                             for (int hh = 0; hh < 2; ++hh) {
@@ -925,7 +962,7 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
     if (!d.w) return DRBA_E_ARG;
     if (!d.bias && d.epilogue != 0) return DRBA_E_ARG;
     if (H <= 0 || W <= 0 || OH <= 0 || OW <= 0 || Cin <= 0 || Cin % 16 != 0) return DRBA_E_ARG;
-    if (G < 1 || G > kMaxGroups || T < 1 || T > kMaxTapsTc) return DRBA_E_ARG;
+    if (G < 1 || G > kMaxGroups || T < 1 || T > kMaxTapsTc || G * T > 36) return DRBA_E_ARG;
     if (S != 1 && S != 2) return DRBA_E_ARG;
     if (S == 2 && (H % 2 != 0 || W % 2 != 0)) return DRBA_E_ARG;
     if (d.cout_pad <= 0 || d.cout_pad % 16 != 0 || d.cout <= 0 || d.cout > d.cout_pad) return DRBA_E_ARG;
@@ -982,7 +1019,9 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
         e = getenv("DRBA_TC_PACK"); env_pack = e ? atoi(e) : 1;
         e = getenv("DRBA_TC_HALO_S2"); env_s2 = e ? atoi(e) : 1;
     }
-    bool halo = env_halo && (S == 1 || (S == 2 && env_s2)) && T == 9 && G == 1 && (d.epilogue == 0 || last3x3) && !d.bgemm;
+    // T == 10: canonical 3x3 taps + an identity tap at (0, 0) (ResConv residual through the tensor core; stride 1 only)
+    const bool restap = T == 10 && S == 1 && d.dy[9] == 0 && d.dx[9] == 0;
+    bool halo = env_halo && (S == 1 || (S == 2 && env_s2)) && (T == 9 || restap) && G == 1 && (d.epilogue == 0 || last3x3) && !d.bgemm;
     if (halo)
         for (int t = 0; t < 9; ++t)
             if (d.dy[t] != t / 3 - 1 || d.dx[t] != t % 3 - 1) halo = false;
@@ -1108,6 +1147,9 @@ static int build_layer(const drba_conv_layer& d, int nimg, LayerDev& L, EncodeTi
         // staging pays where rows are wide or the residual would otherwise be fetched chunk by chunk; latency-bound
         // streaming layers (one or two tiles per SM) keep the direct per-pixel path
         L.staged = (env_staged == 2 || (env_staged == 1 && resident && d.epilogue == 0)) ? 1 : 0;
+        static int env_last = -1;
+        if (env_last < 0) { const char* e = getenv("DRBA_TC_LASTSTG"); env_last = e ? atoi(e) : 1; }
+        if (d.epilogue == 1) L.staged = env_last ? 1 : 0;      // lastconv: stores through the staging tile (64-byte runs)
     }
     L.KI = halo ? L.kchunks : T * L.kchunks;
     if (resident) {
@@ -1302,7 +1344,7 @@ int drba_conv_tc_f16(const void* in, int H, int W, int Cin,
                      int epilogue, int act, const void* res, void* out, int out_cstride, int out_os, void* stream)
 {
     if (!in || !w || !bias || !out || !dy || !dx) return DRBA_E_ARG;
-    if (G < 1 || G > kMaxGroups || T < 1 || T > kMaxTapsTc) return DRBA_E_ARG;
+    if (G < 1 || G > kMaxGroups || T < 1 || T > kMaxTapsTc || G * T > 36) return DRBA_E_ARG;
     drba_conv_layer d;
     memset(&d, 0, sizeof(d));
     d.in[0] = in; d.res[0] = res; d.out[0] = out;

@@ -101,8 +101,14 @@ def _packed_input_channels(first):
     return m
 
 
-def _tc_conv3x3(weight, bias, stride, act, device, beta=None, in_map=None):
+def _tc_conv3x3(weight, bias, stride, act, device, beta=None, in_map=None, res_tap=False):
+    """res_tap: append a tenth tap at offset (0, 0) whose weight tile is the identity -- the ResConv's `+ x`
+    (IFNet_HDv3.py:59) is then accumulated by the tensor core, exactly (x * 1.0 in the fp32 accumulator), and the
+    epilogue has no residual to load; the layer is run WITHOUT a `res` pointer."""
     w, b = _pack_conv3x3(weight, bias, beta)           # [9][Cin][Cout]
+    if res_tap:
+        assert stride == 1 and w.shape[1] == w.shape[2] and in_map is None
+        w = torch.cat([w, torch.eye(w.shape[1])[None]], 0)
     T, cin, cout = w.shape
     if in_map is not None:                             # permute / pad the input channels
         wm = torch.zeros((T, len(in_map), cout))
@@ -117,7 +123,12 @@ def _tc_conv3x3(weight, bias, stride, act, device, beta=None, in_map=None):
     bp = torch.zeros((1, _pad16(cout)))
     bp[0, :cout] = b
     dy, dx = _taps3x3()
-    return _TcLayer(wp, bp, dy, dx, stride, act, cout, 0, device, cin_real=cin_real)
+    if res_tap:
+        dy, dx = dy + [0], dx + [0]
+    layer = _TcLayer(wp, bp, dy, dx, stride, act, cout, 0, device, cin_real=cin_real)
+    layer.res_tap = bool(res_tap)
+    layer.flop_taps = 9          # algorithmic FLOPs of the 3x3 conv (the identity tap is the residual add)
+    return layer
 
 
 def _tc_lastconv(weight, bias, device):
@@ -212,9 +223,12 @@ class IFNetEngine:
                 self.tc[f"{name}.conv0a"] = _tc_conv3x3(sd[f"{name}.conv0.0.0.weight"], sd[f"{name}.conv0.0.0.bias"], 2, 1, d,
                                                         in_map=_packed_input_channels(name == "block0"))
                 self.tc[f"{name}.conv0b"] = _tc_conv3x3(sd[f"{name}.conv0.1.0.weight"], sd[f"{name}.conv0.1.0.bias"], 2, 1, d)
+                # blocks 3 / 4 (many tiles per SM, epilogue-bound): the residual as an identity tap
+                res_tap = c <= 64 and os.environ.get("DRBA_RES_TAP", "1") != "0"
                 for i in range(8):
                     p = f"{name}.convblock.{i}"
-                    self.tc[f"{name}.res{i}"] = _tc_conv3x3(sd[p + ".conv.weight"], sd[p + ".conv.bias"], 1, 1, d, sd[p + ".beta"])
+                    self.tc[f"{name}.res{i}"] = _tc_conv3x3(sd[p + ".conv.weight"], sd[p + ".conv.bias"], 1, 1, d, sd[p + ".beta"],
+                                                            res_tap=res_tap)
                 # blocks 3 / 4 (64 / 32 channels: one phase's 3x3 weights fit shared memory): the 3x3 form
                 last3 = c <= 64 and os.environ.get("DRBA_LAST3X3", "1") != "0"
                 self.tc[f"{name}.last"] = (_tc_lastconv3x3 if last3 else _tc_lastconv)(sd[f"{name}.lastconv.0.weight"], sd[f"{name}.lastconv.0.bias"], d)
@@ -377,7 +391,8 @@ class IFNetEngine:
             steps.append((self.tc[f"{name}.conv0b"], h2, w2, a, p0, h4, w4, c, None))
             cur, nxt = p0, p1
             for i in range(8):
-                steps.append((self.tc[f"{name}.res{i}"], h4, w4, cur, nxt, h4, w4, c, cur))
+                layer = self.tc[f"{name}.res{i}"]
+                steps.append((layer, h4, w4, cur, nxt, h4, w4, c, None if layer.res_tap else cur))
                 cur, nxt = nxt, cur
             steps.append((self.tc[f"{name}.last"], h4, w4, cur, tmp, h4, w4, tch, None))
             self._conv_program(steps, tag=name)

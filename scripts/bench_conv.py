@@ -94,7 +94,7 @@ def main():
                      (eng16.tc[f"{name}.conv0b"], h2, w2, a, p0, h4, w4, c, None)]
             cur, nxt = p0, p1
             for i in range(8):
-                steps.append((eng16.tc[f"{name}.res{i}"], h4, w4, cur, nxt, h4, w4, c, cur))
+                steps.append((eng16.tc[f"{name}.res{i}"], h4, w4, cur, nxt, h4, w4, c, None if getattr(eng16.tc[f"{name}.res{i}"], "res_tap", False) else cur))
                 cur, nxt = nxt, cur
             steps.append((eng16.tc[f"{name}.last"], h4, w4, cur, tmp, h4, w4, 16, None))
             flops = sum(nimg * 2.0 * getattr(l, "flop_taps", l.G * l.T) * l.cin_real * l.cout * oh * ow for (l, _, _, _, _, oh, ow, _, _) in steps)

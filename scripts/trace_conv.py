@@ -45,7 +45,7 @@ def trace_program(name, trace):
              (eng16.tc[f"{bname}.conv0b"], h2, w2, a, p0, h4, w4, c, None)]
     cur, nxt = p0, p1
     for i in range(8):
-        steps.append((eng16.tc[f"{bname}.res{i}"], h4, w4, cur, nxt, h4, w4, c, cur))
+        steps.append((eng16.tc[f"{bname}.res{i}"], h4, w4, cur, nxt, h4, w4, c, None if getattr(eng16.tc[f"{bname}.res{i}"], "res_tap", False) else cur))
         cur, nxt = nxt, cur
     steps.append((eng16.tc[f"{bname}.last"], h4, w4, cur, tmp, h4, w4, tch, None))
     for _ in range(3):

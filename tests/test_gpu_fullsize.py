@@ -51,7 +51,7 @@ def tf32_off():
 
 def _torch_weight(layer):
     """[cout_pad, cin, 3, 3] fp32 weight and [cout_pad] bias of a packed 3x3 layer (w[1][9][cout_pad][cin])."""
-    w = layer.w[0].float()                                 # [9][cout_pad][cin]
+    w = layer.w[0].float()[:9]                             # [9][cout_pad][cin] (a tenth tap is the ResConv's identity tap)
     return w.permute(1, 2, 0).reshape(w.shape[1], w.shape[2], 3, 3).contiguous(), layer.b[0].float()
 
 
@@ -79,7 +79,8 @@ def test_conv_tc_1080p_layer_vs_torch(tf32_off, key, h, w):
     oh, ow = (h - 1) // s + 1, (w - 1) // s + 1
     res = x if (s == 1 and layer.cin == layer.cout_pad and "res" in key) else None
     out = torch.full((oh, ow, layer.cout_pad), float("nan"), dtype=torch.float16, device="cuda")
-    eng._conv_tc(layer, x, h, w, out, oh, ow, layer.cout_pad, res=res)
+    # (layers with an identity tap add the residual on the tensor core: no `res` pointer)
+    eng._conv_tc(layer, x, h, w, out, oh, ow, layer.cout_pad, res=None if getattr(layer, "res_tap", False) else res)
     wt, b = _torch_weight(layer)
     ref = F.conv2d(x.float().permute(2, 0, 1)[None], wt, b, s, 1)
     if res is not None:
@@ -116,7 +117,7 @@ def test_block_program_1080p_two_images_vs_torch(tf32_off, bi, h, w):
              (eng.tc[f"{name}.conv0b"], h2, w2, a, p0, h4, w4, c, None)]
     cur, nxt = p0, p1
     for i in range(8):
-        steps.append((eng.tc[f"{name}.res{i}"], h4, w4, cur, nxt, h4, w4, c, cur))
+        steps.append((eng.tc[f"{name}.res{i}"], h4, w4, cur, nxt, h4, w4, c, None if getattr(eng.tc[f"{name}.res{i}"], "res_tap", False) else cur))
         cur, nxt = nxt, cur
     steps.append((eng.tc[f"{name}.last"], h4, w4, cur, tmp, h4, w4, 16, None))
     eng._conv_program(steps)
