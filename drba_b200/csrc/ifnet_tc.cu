@@ -3,6 +3,12 @@
 // by op, stays in ifnet.cu under -fmad=false): the result is rounded to fp16 anyway, and the kernel was
 // instruction-issue bound (ncu: 77 % issue active) with a separate multiply and add per tap and channel.
 #include "ifnet_common.cuh"
+#ifndef DRBA_ASM_MINB4
+#define DRBA_ASM_MINB4 10
+#endif
+#ifndef DRBA_ASM_MINB1
+#define DRBA_ASM_MINB1 12
+#endif
 
 namespace drba {
 
@@ -56,8 +62,10 @@ constexpr int kAsmTile = 32;   // output pixels per CTA
 // spread over the banks
 __device__ __forceinline__ int tile_slot(int px, int c) { return px * 8 + ((c + 2 * px) & 7); }
 
+// (min blocks per SM: the kernel is latency / L1 bound -- ncu r2: 42 % occupancy at 72 registers, issue 66 %, L1 wavefronts 65 % --
+// so registers are capped for occupancy: 48 (s >= 2) / 40 (s = 1) measured best: block-input time 0.727 -> 0.691 ms per window)
 template <int NP>
-__global__ void __launch_bounds__(kIfThreads)
+__global__ void __launch_bounds__(kIfThreads, NP == 4 ? DRBA_ASM_MINB4 : DRBA_ASM_MINB1)
 ifnet_assemble_v2_kernel(const AssembleParams p)
 {
     __shared__ __align__(16) uint4 tile[kAsmTile * 8];
