@@ -68,6 +68,7 @@ class RIFE:
         self.address_graphs = os.environ.get("DRBA_ADDRESS_GRAPHS", "1") != "0"
         self._graphs = {}
         self._agraphs, self._aseen, self._pool = {}, {}, None
+        self._ause, self._atick = {}, 0       # last replay tick per address graph (least-recently-used eviction)
         self.captures = 0          # graphs captured so far (a driver can warm up until this stops growing)
         self._capture_stream = None
 
@@ -105,11 +106,15 @@ class RIFE:
 
     # ---- address-keyed graphs ----------------------------------------------------------------------------------
     # The generic graph of a window shape reads static input buffers: every window copies three frames (75 MB at
-    # 1080p) and the `reuse` tuple (167 MB) into them.  A driver loop hands the same few buffers round and round (a
-    # frame ring, and `reuse` = the previous graph's own output buffers), so a window whose (shape, timestamps, input
-    # ADDRESSES) combination has been seen before gets a graph captured directly on those addresses: a replay reads
-    # whatever the caller's tensors hold now -- no copies, no staleness (a key only matches while live tensors of
-    # the same shape and dtype sit at those addresses).  All graphs share one memory pool.
+    # 1080p) and the `reuse` tuple (167 MB) into them.  A driver loop hands the same few FRAME buffers round and round
+    # (a frame ring), so a window whose (shape, timestamps, frame ADDRESSES) combination has been seen before gets a
+    # graph captured directly on those frame tensors and on the `reuse` tensors of that moment (the previous graph's
+    # own outputs): a replay reads whatever the frames hold now, and `reuse` is copied only when the caller's tensors
+    # are not the captured ones.  In a cyclic driver every graph but one per cycle follows the graph it followed at
+    # capture time, so one window per cycle pays the 167 MB copy and the others none.
+    # (Round 2, first version: the key also held the `reuse` addresses.  Every new graph owns new output buffers, so
+    # the next window's key was new again: the table never closed, filled up with transient graphs, and a second
+    # caller on the same model -- bench.py's end-to-end loop -- ran on the generic graph: 2.22 instead of 2.08 ms.)
     MAX_ADDRESS_GRAPHS = 64
 
     def _address_key(self, key, frames, reuse):
@@ -121,8 +126,24 @@ class RIFE:
             for r in reuse:
                 if not torch.is_tensor(r):
                     return None
-                k += (r.data_ptr(), r.dtype, tuple(r.shape), tuple(r.stride()))
+                k += (r.dtype, tuple(r.shape), tuple(r.stride()))
         return k
+
+    @staticmethod
+    def _copy_reuse(s_reuse, reuse):
+        """reuse -> the buffers a graph reads.  `reuse` may alias those buffers (the f1 of the previous window IS one of
+        them and belongs in another now): copies that read a static buffer go first, from a snapshot when more than one
+        of them could chain."""
+        static = {d.data_ptr() for d in s_reuse}
+        pending = [(d, s) for d, s in zip(s_reuse, reuse) if d.data_ptr() != s.data_ptr()]
+        first = [(d, s) for d, s in pending if s.data_ptr() in static]
+        if len(first) > 1:
+            first = [(d, s.clone()) for d, s in first]
+        for d, s in first:
+            d.copy_(s)
+        for d, s in pending:
+            if s.data_ptr() not in static:
+                d.copy_(s)
 
     def _drba_graphed(self, I0, I1, I2, ts, reuse, linear):
         ts_key = tuple(float(t) for t in ts)
@@ -137,12 +158,20 @@ class RIFE:
             if hit is None:
                 seen = self._aseen.get(akey, 0) + 1
                 self._aseen[akey] = seen
-                if seen >= 2 and len(self._agraphs) < self.MAX_ADDRESS_GRAPHS:
+                if seen >= 2:
+                    if len(self._agraphs) >= self.MAX_ADDRESS_GRAPHS:
+                        victim = min(self._ause, key=self._ause.get)      # least recently replayed graph out
+                        self._ause.pop(victim)
+                        self._agraphs.pop(victim)
                     hit = self._capture_on_addresses(akey, frames, ts, reuse, linear)
                 elif len(self._aseen) > 4096:
                     self._aseen.clear()
             if hit is not None:
-                graph, outs, new_reuse, passthrough, n_kernels = hit
+                graph, outs, new_reuse, passthrough, n_kernels, cap_reuse = hit
+                self._atick += 1
+                self._ause[akey] = self._atick
+                if reuse:
+                    self._copy_reuse(cap_reuse, reuse)
                 graph.replay()
                 _lib.count(n_kernels)
                 _lib.check_async("RIFE window graph")
@@ -155,19 +184,7 @@ class RIFE:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src.float())
         if reuse:
-            # `reuse` may alias this graph's own static inputs (the f1 of the previous window of the same shape IS
-            # s_reuse[2], and belongs in s_reuse[3] now): copies that read a static buffer go first, from a
-            # snapshot when more than one of them could chain
-            static = {d.data_ptr() for d in s_reuse}
-            pending = [(d, s) for d, s in zip(s_reuse, reuse) if d.data_ptr() != s.data_ptr()]
-            first = [(d, s) for d, s in pending if s.data_ptr() in static]
-            if len(first) > 1:
-                first = [(d, s.clone()) for d, s in first]
-            for d, s in first:
-                d.copy_(s)
-            for d, s in pending:
-                if s.data_ptr() not in static:
-                    d.copy_(s)
+            self._copy_reuse(s_reuse, reuse)
         graph.replay()
         _lib.count(n_kernels)      # kernels inside the replayed graph (recorded at capture)
         _lib.check_async("RIFE window graph")
@@ -197,8 +214,10 @@ class RIFE:
         n_kernels = _lib.KERNEL_LAUNCHES - k0
         _lib.count(-n_kernels)     # capture records, it does not execute
         passthrough = [next((k for k, f in enumerate(frames) if o is f), -1) for o in outs]
-        hit = (graph, outs, new_reuse, passthrough, n_kernels)
+        hit = (graph, outs, new_reuse, passthrough, n_kernels, r)      # r: the `reuse` tensors the graph reads (kept alive)
         self._agraphs[akey] = hit
+        self._atick += 1
+        self._ause[akey] = self._atick
         self.captures += 1
         return hit
 

@@ -153,8 +153,8 @@ def frame_egress_u8(frame, src_size, out=None):
 class FrameIO:
     """Double-buffered host <-> device frame traffic around the interpolation stream.
 
-    upload(np/pinned uint8 frame) -> float net-input tensor: H2D copy + ingest kernel on a copy stream;
-    download(float frame) -> pinned uint8 host buffer: egress kernel + D2H copy on a second copy stream.
+    upload(np/pinned uint8 frame) -> float net-input tensor: H2D copy on a copy stream, ingest kernel on the caller's;
+    download(float frame) -> pinned uint8 host buffer: egress kernel on the caller's stream, D2H copy on a second copy stream.
     Both are ordered against the caller's current stream with events only (no host synchronisation);
     `drain()` waits for all downloads issued so far.  Replaces the reference's synchronous
     to_inp / to_out (tools.py:59-68), whose fp32 D2H moves 4x the bytes."""
@@ -170,6 +170,7 @@ class FrameIO:
         self._out_host = [torch.empty((h, w, 3), dtype=torch.uint8).pin_memory() for _ in range(out_depth)]
         self._out_done = [None] * out_depth
         self._in_free = [None] * depth      # event: the compute stream has finished reading slot k
+        self._u8_free = [None] * depth      # event: the ingest kernel has consumed the uint8 staging buffer of slot k
         self._i = self._o = 0
         self.h2d_bytes = self.d2h_bytes = 0
 
@@ -183,12 +184,20 @@ class FrameIO:
         cur = torch.cuda.current_stream(self.device)
         if self._in_free[k] is not None:
             self.h2d.wait_event(self._in_free[k])
+        if self._u8_free[k] is not None:
+            self.h2d.wait_event(self._u8_free[k])
+        # Only the COPY rides the copy stream; the ingest kernel runs on the caller's stream.  A kernel on a side stream
+        # competes for SMs with the persistent conv programs, whose grid barrier needs all their CTAs resident: measured,
+        # ONE 13 us side-stream kernel per window costs 73 us of window time, the same kernel in stream 14 us.
         with torch.cuda.stream(self.h2d):
             self._in_u8[k].copy_(host_u8, non_blocking=True)
-            frame_ingest_u8(self._in_u8[k], self.dst, out=self._in_f[k])
             ev = torch.cuda.Event()
             ev.record(self.h2d)
         cur.wait_event(ev)
+        frame_ingest_u8(self._in_u8[k], self.dst, out=self._in_f[k])
+        used = torch.cuda.Event()
+        used.record(cur)
+        self._u8_free[k] = used             # the staging buffer may be overwritten once the ingest kernel has read it
         self.h2d_bytes += host_u8.numel()
         self._last_slot = k
         return self._in_f[k]
@@ -215,12 +224,14 @@ class FrameIO:
         self._o += 1
         if self._out_done[k] is not None:
             self._out_done[k].synchronize()         # host buffer k is about to be overwritten
+        cur = torch.cuda.current_stream(self.device)
+        if self._out_done[k] is not None:
+            cur.wait_event(self._out_done[k])       # the previous D2H out of device buffer k has finished (host already waited)
+        frame_egress_u8(frame, self.src, out=self._out_u8[k])      # on the caller's stream (see upload)
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
+        ev.record(cur)
         self.d2h.wait_event(ev)
         with torch.cuda.stream(self.d2h):
-            frame.record_stream(self.d2h)
-            frame_egress_u8(frame, self.src, out=self._out_u8[k])
             self._out_host[k].copy_(self._out_u8[k], non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.d2h)

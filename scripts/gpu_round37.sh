@@ -1,0 +1,5 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_cli.py -x -q 2>&1 | tail -3
+DRBA_E2E_EVENTS=1 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-gpu-reference --no-other-configs 2>gpurun_out/e.err | python -c "
+import sys,json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], json.dumps(d['e2e']))"; grep 'e2e events' gpurun_out/e.err | tail -1
