@@ -93,9 +93,9 @@ class RIFE:
         f0 = self.ifnet.encode(a3) if f0 is None else _nhwc(f0)
         f1 = self.ifnet.encode(b3) if f1 is None else _nhwc(f1)
         flow = self.ifnet.block0_flow(a3, b3, f0, f1, 0.5, self.scale_list[0])
-        flow01 = rife_invert_flow(flow[:, :2])
-        flow10 = rife_invert_flow(flow[:, 2:])
-        return flow01, flow10, _nchw_view(f0), _nchw_view(f1)
+        # both directions in one call: the planar [1, 4, H, W] flow is a batch of two [2, H, W] fields
+        inv = rife_invert_flow(flow.view(2, 2, flow.shape[2], flow.shape[3]))
+        return inv[0:1], inv[1:2], _nchw_view(f0), _nchw_view(f1)
 
     @torch.inference_mode()
     def inference_ts_drba(self, I0, I1, I2, ts, reuse=None, linear=False):

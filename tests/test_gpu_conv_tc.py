@@ -64,16 +64,18 @@ def test_conv3x3_tc_vs_torch(cin, cout, h, w, stride, res):
     assert (err <= tol).all(), f"max err {err.max().item():.4g} at |ref| max {ref.abs().max().item():.3g}"
 
 
-@pytest.mark.parametrize("cin,h,w", [(32, 16, 32), (64, 17, 30), (192, 9, 15), (96, 34, 60)])
-def test_lastconv_tc_vs_torch(cin, h, w):
-    """ConvTranspose2d(cin, 52, 4, 2, 1) + PixelShuffle(2) (IFNet_HDv3.py:79-82)."""
-    from drba_b200.ifnet import _tc_lastconv
+@pytest.mark.parametrize("cin,h,w,form", [(32, 16, 32, "phases"), (64, 17, 30, "phases"), (192, 9, 15, "phases"), (96, 34, 60, "phases"),
+                                          (32, 34, 60, "3x3"), (64, 17, 30, "3x3"), (32, 272, 480, "3x3")])
+def test_lastconv_tc_vs_torch(cin, h, w, form):
+    """ConvTranspose2d(cin, 52, 4, 2, 1) + PixelShuffle(2) (IFNet_HDv3.py:79-82): as four phase convs of four taps, and as
+    one zero-padded 3x3 conv with 4 x 64 columns (halo mode, one phase resident per CTA, stores through the staging tile)."""
+    from drba_b200.ifnet import _tc_lastconv, _tc_lastconv3x3
     eng = _engine()
     g = torch.Generator(device="cpu").manual_seed(cin + h)
     x = torch.randn((1, cin, h, w), generator=g)
     wt = torch.randn((cin, 52, 4, 4), generator=g) * (1.0 / (cin * 4)) ** 0.5
     b = torch.randn((52,), generator=g) * 0.1
-    layer = _tc_lastconv(wt, b, "cuda")
+    layer = (_tc_lastconv if form == "phases" else _tc_lastconv3x3)(wt, b, "cuda")
     xh = x.half()
     x_nhwc = xh[0].permute(1, 2, 0).contiguous().cuda()
     out = torch.full((4 * h, 4 * w, 16), float("nan"), dtype=torch.float32, device="cuda")
