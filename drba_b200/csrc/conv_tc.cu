@@ -357,6 +357,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
     uint32_t bres_phase = 0;         // MMA warp: parity of the next resident-weights barrier phase
 
     for (int li = 0; li < nlayers; ++li) {
+        if (threadIdx.x == 0) TC_TRACE(li * 256 + 208);
         const LayerDev& L = prog.L[li];
         // layer constants -> registers (once per layer)
         const int total_tiles = L.total_tiles, mtiles = L.mtiles, nsplits = L.nsplits, G = L.G;
@@ -369,13 +370,10 @@ conv_tc_kernel(const __grid_constant__ Program prog)
         stage = 0;
 
         if (warp == 0) {
+            if (lane == 0) TC_TRACE(li * 256 + 205);
             // ===== activation producer: the whole warp walks the loop, one elected lane issues =====
             const uint32_t a_bytes = (dbg & 2) ? 0u : (uint32_t)(halo == 2 ? 4 * 17 * 9 * Kc * 2 : (pack > 1 ? 10 * 18 * 128 : (halo ? (16 * MT + 2) * 16 * Kc * 2 : MT * kTileM * Kc * 2)));
             const uint32_t s2_sub = ((uint32_t)(17 * 9 * Kc * 2) + 1023u) & ~1023u;      // stride-2 halo: one parity box
-            if (li + 1 < nlayers && elect_one()) {
-                asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].ta[0]) : "memory");
-                asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].tb) : "memory");
-            }
             int tl = 0;
             for (int idx = blockIdx.x; idx < total_tiles; idx += gridDim.x, ++tl) {
                 int m, r;
@@ -389,6 +387,7 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 for (int it = 0; it < KI; ++it) {
                     if (tl < 10 && it < 2 && lane == 0) TC_TRACE(li * 256 + tl * 16 + it * 4 + 0);
                     mbar_wait(&empty_bar[stage], ((pbits >> stage) & 1u) ^ 1u);
+                    if (tl == 0 && it == 0 && lane == 0) TC_TRACE(li * 256 + 207);
                     if (elect_one()) {
                         mbar_expect_tx(&full_bar[stage], a_bytes);
                         if (resident) mbar_arrive(&full_bar[stage]);      // stands in for the weight producer
@@ -415,6 +414,14 @@ conv_tc_kernel(const __grid_constant__ Program prog)
                 }
             }
         } else if (warp == 10) {
+            // the next layer's tensor maps are prefetched HERE, not by the activation producer: there the two prefetches
+            // sat in front of the first TMA of the layer (trace: 1250 cycles between the producer's entry and its first tile)
+            if (li + 1 < nlayers && elect_one()) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].ta[0]) : "memory");
+                if (prog.nimg > 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].ta[1]) : "memory");
+                asm volatile("prefetch.tensormap [%0];" ::"l"(&prog.L[li + 1].tb) : "memory");
+            }
+            __syncwarp();
             // ===== weight producer (streaming mode only; resident weights were issued at the layer boundary) =====
             if (!resident) {
                 const uint32_t b_bytes = (dbg & 4) ? 0u : (uint32_t)(ntile * Kc * 2);

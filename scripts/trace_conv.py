@@ -71,7 +71,8 @@ def trace_program(name, trace):
         drains = [rel(v) for tl in tiles for v in (t[base + tl * 16 + 9], t[base + tl * 16 + 11]) if v]
         print(f" layer {li:2d}: start {prev_out} first_tma {rel(t[base + 1])} first_full {rel(t[base + 2])} mma_issued[0] {rel(t[base + 3])} "
               f"mma_issued[{last}] {rel(t[base + last * 16 + 3])} last_drain {max(drains) if drains else None} "
-              f"barrier_in {rel(t[base + 202])} barrier_out {rel(t[base + 203])} post_barrier_sync {rel(t[base + 204])}"
+              f"barrier_in {rel(t[base + 202])} barrier_out {rel(t[base + 203])} | loop_top {rel(t[base + 208])} consts_done {rel(t[base + 205])} "
+              f"tile0_prewait {rel(t[base + 0])} tile0_ring_ok {rel(t[base + 207])} |"
               f"  mma_issue_times {[rel(t[base + tl * 16 + 3]) for tl in tiles]}")
         if t[base + 203]:
             prev_out = rel(t[base + 203])
