@@ -289,6 +289,56 @@ def test_address_keyed_graphs_match_eager(precision):
         assert d <= 2e-3, f"output {k}: graphs vs eager differ by {d:.3g}"
 
 
+def test_address_graph_table_is_bounded_and_second_caller_gets_graphs(monkeypatch):
+    """The address-keyed table must stay small and keep serving NEW callers: (a) two loops over two different frame
+    rings on one model (bench.py's device-resident loop, then its end-to-end loop) must both end up replaying address
+    graphs -- the first round-2 version keyed on the `reuse` addresses as well, never closed its cycle, filled the table
+    with transients and left the second caller on the generic graph; (b) with a table smaller than the number of
+    distinct windows the least recently used graphs are evicted and results still equal the eager path."""
+    from drba_b200.rife import RIFE
+    from drba_b200.weights import synth_ifnet_state
+    torch.set_grad_enabled(False)
+    state = synth_ifnet_state(0)
+    g = torch.Generator(device="cpu").manual_seed(17)
+    h, w = 64, 128
+    base = F.interpolate(torch.rand((1, 3, h // 8 + 16, w // 8 + 24), generator=g), scale_factor=8, mode="bilinear")
+    tss = [np.array([0.6, 1.0, 1.4]), np.array([0.8, 1.2])]
+
+    def run(m, ring, passes, off):
+        bufs = [torch.empty((1, 3, h, w), device="cuda") for _ in range(ring)]
+        res, reuse, j = [], None, 0
+        for p in range(passes):
+            for k in range(ring):
+                bufs[k].copy_(base[:, :, 2 * k + 3 * p + off:2 * k + 3 * p + off + h, 3 * k + 5 * p:3 * k + 5 * p + w])
+            for k in range(ring):
+                o, reuse = m.inference_ts_drba(bufs[k], bufs[(k + 1) % ring], bufs[(k + 2) % ring], tss[j % 2], reuse, True)
+                res += [x.clone() for x in o]
+                j += 1
+        torch.cuda.synchronize()
+        return res
+
+    eager = RIFE(state=state, device="cuda", precision="fp16", graphs=False)
+    m = RIFE(state=state, device="cuda", precision="fp16", graphs=True)
+    a = run(m, 8, 4, 0)
+    n_first = len(m._agraphs)
+    assert 8 <= n_first <= 16, f"first caller: {n_first} address graphs for a ring of 8 (the cycle must close)"
+    c0 = m.captures
+    b = run(m, 4, 6, 1)                      # a second caller with its own ring on the same model
+    assert len(m._agraphs) <= n_first + 8
+    assert m.captures - c0 <= 8, "second caller keeps capturing: its address cycle does not close"
+    for got, want in ((a, run(eager, 8, 4, 0)), (b, run(eager, 4, 6, 1))):
+        assert len(got) == len(want)
+        for k, (x, y) in enumerate(zip(got, want)):
+            assert float((x - y).abs().max()) <= 2e-3, f"output {k}"
+    # (b) a table of 3 graphs for 8 distinct windows: eviction on every capture, same results
+    monkeypatch.setattr(RIFE, "MAX_ADDRESS_GRAPHS", 3)
+    m2 = RIFE(state=state, device="cuda", precision="fp16", graphs=True)
+    c = run(m2, 8, 3, 0)
+    assert len(m2._agraphs) <= 3
+    for k, (x, y) in enumerate(zip(c, run(eager, 8, 3, 0))):
+        assert float((x - y).abs().max()) <= 2e-3, f"evicting table, output {k}"
+
+
 @pytest.mark.parametrize("size", [(64, 128), (1088, 1920)])
 def test_lazy_flow_terms_match_materialised_flow(size):
     """Blocks 1 and 2 evaluate the flow as a sum of up-sampled lastconv outputs at their own sample positions and the
