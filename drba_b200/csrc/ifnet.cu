@@ -50,32 +50,6 @@ ifnet_flow_accum_kernel(const Tmp13 t, float* __restrict__ flow, float* __restri
     }
 }
 
-// flow = s0 * up(tmp0) + s1 * up(tmp1) + s2 * up(tmp2), summed in block order: what three consecutive
-// ifnet_flow_accum launches leave behind, in ONE write-only pass (the coarse blocks' assemble kernels evaluate
-// the flow at their own sample positions, so the first full-resolution flow is needed before block 3 only)
-__global__ void __launch_bounds__(256)
-ifnet_flow_sum_kernel(const Tmp13 t0, const Tmp13 t1, const Tmp13 t2, int nterms, float* __restrict__ flow, int H, int W)
-{
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= H * W) return;
-    const int y = idx / W, x = idx - y * W;
-    float o[4];
-    up_tmp<1, 0, 4>(t0, y, x, o);
-    float fs = (float)t0.s;
-    float4 f = make_float4(o[0] * fs, o[1] * fs, o[2] * fs, o[3] * fs);
-    if (nterms > 1) {
-        up_tmp<1, 0, 4>(t1, y, x, o);
-        fs = (float)t1.s;
-        f.x = f.x + o[0] * fs; f.y = f.y + o[1] * fs; f.z = f.z + o[2] * fs; f.w = f.w + o[3] * fs;
-    }
-    if (nterms > 2) {
-        up_tmp<1, 0, 4>(t2, y, x, o);
-        fs = (float)t2.s;
-        f.x = f.x + o[0] * fs; f.y = f.y + o[1] * fs; f.z = f.z + o[2] * fs; f.w = f.w + o[3] * fs;
-    }
-    reinterpret_cast<float4*>(flow)[idx] = f;
-}
-
 // ---- block input assembly ---------------------------------------------------------------
 // Mean of the (up to) 4 sampled positions in the order bilinear resampling adds them:
 // 0.5*(0.5*a + 0.5*b) + 0.5*(0.5*c + 0.5*d) == ((a + b) + (c + d)) * 0.25 exactly in fp32.
@@ -303,7 +277,7 @@ int drba_ifnet_flow_sum(const float* tmp0, int s0, const float* tmp1, int s1, co
             t[k].p = tp[k]; t[k].s = ss[k]; t[k].h13 = H / ss[k]; t[k].w13 = W / ss[k];
         }
     }
-    ifnet_flow_sum_kernel<<<cdiv((size_t)H * W, 256), 256, 0, as_stream(stream)>>>(t[0], t[1], t[2], nterms, flow, H, W);
+    launch_flow_sum_tc(t[0], t[1], t[2], nterms, flow, H, W, as_stream(stream));
     DRBA_RETURN_IF_LAUNCH_FAILED();
     return DRBA_OK;
 }

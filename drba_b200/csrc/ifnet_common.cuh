@@ -192,5 +192,6 @@ __device__ __forceinline__ float4 load_flow(const AssembleParams& p, int y, int 
 
 // ifnet_tc.cu: the L1-friendly NHWC fp16 kernel
 void launch_assemble_tc(const AssembleParams& p, cudaStream_t st);
+void launch_flow_sum_tc(const Tmp13& t0, const Tmp13& t1, const Tmp13& t2, int nterms, float* flow, int H, int W, cudaStream_t st);
 
 }  // namespace drba

@@ -204,6 +204,38 @@ ifnet_assemble_v2_kernel(const AssembleParams p)
     }
 }
 
+// (tensor-core engine only, hence in this FMA-contracting file: the kernel is issue-bound on three bilinear up-samplings per pixel)
+// flow = s0 * up(tmp0) + s1 * up(tmp1) + s2 * up(tmp2), summed in block order: what three consecutive
+// ifnet_flow_accum launches leave behind, in ONE write-only pass (the coarse blocks' assemble kernels evaluate
+// the flow at their own sample positions, so the first full-resolution flow is needed before block 3 only)
+__global__ void __launch_bounds__(256)
+ifnet_flow_sum_kernel(const Tmp13 t0, const Tmp13 t1, const Tmp13 t2, int nterms, float* __restrict__ flow, int H, int W)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= H * W) return;
+    const int y = idx / W, x = idx - y * W;
+    float o[4];
+    up_tmp<1, 0, 4>(t0, y, x, o);
+    float fs = (float)t0.s;
+    float4 f = make_float4(o[0] * fs, o[1] * fs, o[2] * fs, o[3] * fs);
+    if (nterms > 1) {
+        up_tmp<1, 0, 4>(t1, y, x, o);
+        fs = (float)t1.s;
+        f.x = f.x + o[0] * fs; f.y = f.y + o[1] * fs; f.z = f.z + o[2] * fs; f.w = f.w + o[3] * fs;
+    }
+    if (nterms > 2) {
+        up_tmp<1, 0, 4>(t2, y, x, o);
+        fs = (float)t2.s;
+        f.x = f.x + o[0] * fs; f.y = f.y + o[1] * fs; f.z = f.z + o[2] * fs; f.w = f.w + o[3] * fs;
+    }
+    reinterpret_cast<float4*>(flow)[idx] = f;
+}
+
+void launch_flow_sum_tc(const Tmp13& t0, const Tmp13& t1, const Tmp13& t2, int nterms, float* flow, int H, int W, cudaStream_t st)
+{
+    ifnet_flow_sum_kernel<<<cdiv((size_t)H * W, 256), 256, 0, st>>>(t0, t1, t2, nterms, flow, H, W);
+}
+
 void launch_assemble_tc(const AssembleParams& p, cudaStream_t st)
 {
     const dim3 grid(cdiv((size_t)p.w, kAsmTile), (unsigned)p.h);
