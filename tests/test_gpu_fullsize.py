@@ -209,6 +209,36 @@ def test_rife_drba_windows_1080p_vs_oracle(precision, clip):
         assert frac < (2e-3 if precision == "fp32" else 3e-2)
 
 
+@pytest.mark.parametrize("h,w,scale", [(768, 1280, 1.0), (576, 1024, 1.0), (320, 576, 1.0), (1152, 1920, 0.5), (2176, 3840, 0.5)])
+def test_rife_drba_window_other_sizes_vs_oracle(h, w, scale):
+    """The conv engine picks tiles, N splits, resident / streamed weights and halo modes per layer SIZE (narrow resident N
+    splits for the coarse levels, packed halo boxes, grid-vs-split checks): one DRBA window of the fp16 engine at sizes
+    other than the benchmarked one -- 720p (768 rows), 1024 x 576, a small frame, 1080p and 4K at scale 0.5 (GMFSS_union's RIFE
+    configuration) -- against the CPU oracle.  models/rife.py:77-109.  Bar: PSNR >= 60 dB, <= 5e-4 of the pixels off by
+    more than 2/255 (the bars of the 1080p test)."""
+    import bench
+    from drba_b200.rife import RIFE
+    from oracle.ifnet import RIFEOracle
+    torch.set_grad_enabled(False)
+    state, wtag = _state()
+    frames = bench.synth_clip(3, h, w, 1000, "cpu")
+    ts = np.array([0.6, 1.0, 1.4])
+    want, _ = RIFEOracle(state, scale=scale).inference_ts_drba(frames[0], frames[1], frames[2], ts, None, True)
+    m = RIFE(state=state, scale=scale, device="cuda", precision="fp16")
+    dev = [f.cuda() for f in frames]
+    got, _ = m.inference_ts_drba(dev[0], dev[1], dev[2], ts, None, True)
+    torch.cuda.synchronize()
+    for t, a, b in zip(ts, got, want):
+        if t == 1.0:
+            continue
+        a = a.float().cpu()
+        p = _psnr(a, b)
+        bad = float(((a - b).abs() > 2.0 / 255.0).float().mean())
+        _record(test="rife_window_other_sizes", size=[h, w], scale=scale, weights=wtag, t=float(t), psnr=p, frac_gt_2_255=bad)
+        assert p >= 60.0, f"{h}x{w} scale {scale} t={t}: PSNR {p:.1f} dB"
+        assert bad <= 5e-4, f"{h}x{w} scale {scale} t={t}: {bad:.2e} of the pixels off by > 2/255"
+
+
 @pytest.mark.parametrize("precision", ["fp16", "fp32"])
 def test_graph_replay_same_key_windows_match_eager(precision):
     """Three and more consecutive windows with IDENTICAL timestamp lists (-t N, or 30 -> 60 fps): the graph of that
